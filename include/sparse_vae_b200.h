@@ -1,0 +1,140 @@
+/*
+ * sparse_vae_b200 -- C ABI of the B200-native hot path of norabelrose/sparse-vae.
+ *
+ * libsvae_b200.so exports exactly the entry points declared here: plain pointers, sizes and POD
+ * descriptors, no torch / C++ types.  All device pointers are borrowed for the duration of the
+ * stream-ordered launch; the caller (PyTorch on the host side) owns every buffer, output and scratch.
+ * Every launch goes to the `stream` argument (a cudaStream_t passed as void*); no entry point
+ * synchronises the device.  Functions return 0 on success and a negative SVAE_ERR_* otherwise;
+ * svae_last_error() returns a thread-local, human-readable description of the last failure.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   svae_layout_*      SparseAttention.get_master_layout            sparse_vae/core/sparse_attention.py:38-59
+ *                      + LUT builders of the Triton ops             sparse_vae/core/sparse_matmul.py:133-144,251-326
+ *   svae_attn_fwd      SparseAttention.__call__ = sdd->softmax->dsd sparse_vae/core/sparse_attention.py:75-92
+ *                      (triton.ops.blocksparse.matmul / softmax, triton==1.1.0, requirements.txt:11)
+ *   svae_attn_bwd      autograd of the above                        sparse_vae/core/sparse_matmul.py:463-488
+ *   svae_bottleneck_*  ConditionalGaussian.forward                  sparse_vae/core/conditional_gaussian.py:18-30
+ *                      + ContinuousVAE.sample_z                     sparse_vae/core/continuous_autoencoder.py:42-52
+ *                      + torch.distributions.Normal.rsample (Philox stream of at::native normal_)
+ * There is no CPU implementation behind this ABI: host pointers are rejected by the host-side wrappers
+ * and the library needs an sm_100a device.
+ */
+#ifndef SPARSE_VAE_B200_H_
+#define SPARSE_VAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVAE_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SVAE_API __attribute__((visibility("default")))
+#else
+#define SVAE_API
+#endif
+
+/* element types of q/k/v/out and of the bottleneck's mu|logvar input */
+#define SVAE_DTYPE_F32  0   /* exact CUDA-core path (fp32 FFMA); parity mode, 1e-4 */
+#define SVAE_DTYPE_BF16 1   /* tcgen05 / TMEM / TMA path */
+#define SVAE_DTYPE_F16  2   /* tcgen05 / TMEM / TMA path */
+
+#define SVAE_OK                0
+#define SVAE_ERR_INVALID      -1   /* bad argument (shape, stride, dtype, alignment) */
+#define SVAE_ERR_UNSUPPORTED  -2   /* valid request outside what the kernels implement */
+#define SVAE_ERR_CUDA         -3   /* CUDA runtime / driver error, see svae_last_error() */
+#define SVAE_ERR_DEVICE       -4   /* not an sm_100 device */
+
+/* svae_attn_desc.flags */
+#define SVAE_ATTN_FORCE_EXACT  1   /* run 16-bit inputs through the exact CUDA-core path (cross-check / debugging) */
+
+/* Block-sparse attention problem.  Tensors are [batch, heads, seq_len, head_dim] with arbitrary
+ * batch/head/row strides (in ELEMENTS) and unit inner stride -- the reference hands the op strided
+ * views of [B, L, H*Dh] (core/attention.py:76). */
+typedef struct svae_attn_desc {
+  int32_t batch, heads, seq_len, head_dim;
+  int32_t dtype;          /* SVAE_DTYPE_* of q, k, v, out and the gradients */
+  int32_t block_size;     /* must be 32 (SparseAttention.block_size) */
+  int32_t window_size;    /* SparseAttention.window_size */
+  int32_t causal;         /* SparseAttention.causal */
+  int32_t include_cls;    /* SparseAttention.include_cls */
+  int32_t flags;          /* SVAE_ATTN_* */
+  float   scale;          /* softmax scale, reference: head_dim ** -0.5 */
+  int32_t reserved;
+  int64_t q_stride[3], k_stride[3], v_stride[3], o_stride[3];       /* {batch, head, row} */
+  int64_t do_stride[3], dq_stride[3], dk_stride[3], dv_stride[3];   /* backward only */
+} svae_attn_desc;
+
+SVAE_API int svae_abi_version(void);
+SVAE_API const char* svae_last_error(void);
+/* 0 if the current CUDA device can run the kernels (compute capability 10.x), else SVAE_ERR_DEVICE */
+SVAE_API int svae_device_check(void);
+
+/* ---- layout (host only; bit-exact with get_master_layout()[..., :nb, :nb]) ------------------- */
+/* non-zero blocks per head */
+SVAE_API int64_t svae_layout_nnz(int32_t num_blocks, int32_t window_size, int32_t causal, int32_t include_cls);
+/* Any output pointer may be NULL.  layout: [num_heads, nb, nb] int64 0/1.  row_ptr[nb+1] / col_idx[nnz]
+ * enumerate each block-row's key blocks in `layout.nonzero()` order; colT_ptr[nb+1] / rowT_idx[nnz]
+ * enumerate each key block's query block-rows (used by the dK/dV pass). */
+SVAE_API int svae_layout_build(int32_t num_blocks, int32_t window_size, int32_t causal, int32_t include_cls,
+                      int32_t num_heads, int64_t* layout, int32_t* row_ptr, int32_t* col_idx,
+                      int32_t* colT_ptr, int32_t* rowT_idx);
+
+/* ---- attention ------------------------------------------------------------------------------ */
+/* out = softmax(scale * q k^T + key_padding_mask[b, key]; layout, causal) v, fused, S/P never reach HBM.
+ * key_padding_mask: additive fp32 [batch, seq_len] (0 / -inf / -1e7 ...) or NULL.
+ * lse: fp32 [batch, heads, seq_len] natural-log-sum-exp of every row (saved for backward). */
+SVAE_API int svae_attn_fwd(const svae_attn_desc* desc, const void* q, const void* k, const void* v,
+                  const float* key_padding_mask, void* out, float* lse, void* stream);
+
+SVAE_API size_t svae_attn_bwd_workspace_bytes(const svae_attn_desc* desc);
+/* dq, dk, dv (same dtype as q) from dout; workspace: device scratch of at least
+ * svae_attn_bwd_workspace_bytes(desc) bytes, 256-byte aligned, contents ignored on entry. */
+SVAE_API int svae_attn_bwd(const svae_attn_desc* desc, const void* q, const void* k, const void* v,
+                  const void* out, const void* dout, const float* lse, const float* key_padding_mask,
+                  void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug variant of svae_attn_fwd for the tcgen05 path: additionally dumps the raw scores
+ * S = q k^T (before scale/masks) of every query row against its tile's key slots to
+ * s_dump[batch, heads, seq_len, slots*32] (fp32; slots = svae_attn_fwd_slots(desc)). */
+SVAE_API int svae_attn_fwd_slots(const svae_attn_desc* desc);
+SVAE_API int svae_attn_fwd_debug(const svae_attn_desc* desc, const void* q, const void* k, const void* v,
+                        const float* key_padding_mask, void* out, float* lse, float* s_dump, void* stream);
+
+/* ---- latent bottleneck ---------------------------------------------------------------------- */
+#define SVAE_BOTTLENECK_WORKSPACE_BYTES 8448
+/* mulogvar: [rows, 2*latent] (dtype), mu = [:, :latent], logvar = [:, latent:], row stride `ld` elements.
+ * token_counts: int64 [rows].  eps for element (row, d) is the value torch's CUDA `normal_` would write
+ * to element row*latent + d of a [rows*latent] tensor of `dtype` with Philox (seed, offset) on a device
+ * with `sm_count` SMs / `max_threads_per_sm` -- i.e. bit-identical to Normal(mu, sigma).rsample().
+ * Outputs (fp32, contiguous): z[rows, latent], sigma[rows, latent], kl_elem[rows, latent] (may be NULL),
+ * raw_kl[rows], kl[1] = mean(raw_kl / token_counts).  `workspace`: device scratch of
+ * SVAE_BOTTLENECK_WORKSPACE_BYTES bytes, zero-filled ONCE by the caller before its first use; the kernel
+ * leaves it zeroed again (deterministic two-level reduction of kl; no atomics on floating point). */
+SVAE_API int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+                        int64_t rows, int32_t latent, uint64_t philox_seed, uint64_t philox_offset,
+                        int32_t sm_count, int32_t max_threads_per_sm,
+                        float* z, float* sigma, float* kl_elem, float* raw_kl, float* kl,
+                        void* workspace, void* stream);
+/* Number the Philox offset must be advanced by after the call (ATen calc_execution_policy). */
+SVAE_API uint64_t svae_bottleneck_philox_increment(int64_t rows, int32_t latent, int32_t sm_count,
+                                          int32_t max_threads_per_sm);
+/* d_mulogvar[rows, 2*latent] (dtype, row stride ld_out) from upstream gradients (any may be NULL = zero):
+ * dz[rows, latent], dsigma[rows, latent], dkl_elem[rows, latent], draw_kl[rows] (fp32), dkl[1] (fp32, device).
+ *   d mu     = dz + g mu                                 g = dkl_elem + draw_kl[row] + dkl / (rows * token_counts[row])
+ *   d logvar = (dz eps + dsigma) sigma / 2 + g (exp(logvar) - 1) / 2
+ * eps is regenerated from (seed, offset); nothing but mu|logvar is re-read. */
+SVAE_API int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+                        int64_t rows, int32_t latent, uint64_t philox_seed, uint64_t philox_offset,
+                        int32_t sm_count, int32_t max_threads_per_sm,
+                        const float* dz, const float* dsigma, const float* dkl_elem, const float* draw_kl,
+                        const float* dkl, void* d_mulogvar, int64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SPARSE_VAE_B200_H_ */

@@ -1,0 +1,108 @@
+"""ctypes binding of libsvae_b200.so (include/sparse_vae_b200.h).
+
+The library is the ONLY implementation of the hot path: if it is missing or cannot be loaded the import of
+this module raises -- there is no Python / CPU fallback.  Build it with
+`python -m sparse_vae_b200.csrc.build` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / 'csrc' / 'libsvae_b200.so'
+
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+ATTN_FORCE_EXACT = 1
+BOTTLENECK_WORKSPACE_BYTES = 8448
+ABI_VERSION = 1
+
+_TORCH_TO_SVAE = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
+
+EXPORTS = (
+    'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
+    'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
+    'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
+)
+
+
+class AttnDesc(C.Structure):
+    """struct svae_attn_desc"""
+    _fields_ = [
+        ('batch', C.c_int32), ('heads', C.c_int32), ('seq_len', C.c_int32), ('head_dim', C.c_int32),
+        ('dtype', C.c_int32), ('block_size', C.c_int32), ('window_size', C.c_int32), ('causal', C.c_int32),
+        ('include_cls', C.c_int32), ('flags', C.c_int32), ('scale', C.c_float), ('reserved', C.c_int32),
+        ('q_stride', C.c_int64 * 3), ('k_stride', C.c_int64 * 3), ('v_stride', C.c_int64 * 3),
+        ('o_stride', C.c_int64 * 3), ('do_stride', C.c_int64 * 3), ('dq_stride', C.c_int64 * 3),
+        ('dk_stride', C.c_int64 * 3), ('dv_stride', C.c_int64 * 3),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sparse-vae hot path has no fallback implementation. "
+            f"Build it with `python -m sparse_vae_b200.csrc.build`.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, u64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
+    desc_p = C.POINTER(AttnDesc)
+    lib.svae_abi_version.restype = C.c_int
+    lib.svae_abi_version.argtypes = []
+    lib.svae_last_error.restype = C.c_char_p
+    lib.svae_last_error.argtypes = []
+    lib.svae_device_check.restype = C.c_int
+    lib.svae_device_check.argtypes = []
+    lib.svae_layout_nnz.restype = i64
+    lib.svae_layout_nnz.argtypes = [i32, i32, i32, i32]
+    lib.svae_layout_build.restype = C.c_int
+    lib.svae_layout_build.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.svae_attn_fwd.restype = C.c_int
+    lib.svae_attn_fwd.argtypes = [desc_p, vp, vp, vp, f32p, vp, f32p, vp]
+    lib.svae_attn_fwd_debug.restype = C.c_int
+    lib.svae_attn_fwd_debug.argtypes = [desc_p, vp, vp, vp, f32p, vp, f32p, f32p, vp]
+    lib.svae_attn_fwd_slots.restype = C.c_int
+    lib.svae_attn_fwd_slots.argtypes = [desc_p]
+    lib.svae_attn_bwd_workspace_bytes.restype = C.c_size_t
+    lib.svae_attn_bwd_workspace_bytes.argtypes = [desc_p]
+    lib.svae_attn_bwd.restype = C.c_int
+    lib.svae_attn_bwd.argtypes = [desc_p, vp, vp, vp, vp, vp, f32p, f32p, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.svae_bottleneck_fwd.restype = C.c_int
+    lib.svae_bottleneck_fwd.argtypes = [vp, i64, i32, vp, i64, i32, u64, u64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.svae_bottleneck_philox_increment.restype = u64
+    lib.svae_bottleneck_philox_increment.argtypes = [i64, i32, i32, i32]
+    lib.svae_bottleneck_bwd.restype = C.c_int
+    lib.svae_bottleneck_bwd.argtypes = [vp, i64, i32, vp, i64, i32, u64, u64, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    if lib.svae_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib.svae_last_error().decode('utf-8', 'replace')
+        exc = ValueError if rc in (-1, -2) else NativeError
+        raise exc(f"{what} failed ({rc}): {msg}")
+
+
+def svae_dtype(dtype: torch.dtype) -> int:
+    try:
+        return _TORCH_TO_SVAE[dtype]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {dtype}; expected float32, bfloat16 or float16") from None
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,316 @@
+// Fused block-sparse attention forward for sm_100a: TMA -> SMEM -> tcgen05.mma (S = Q K^T into TMEM) ->
+// softmax on the TMEM rows (scale, additive key-padding, causal diagonal, band layout) -> P (16-bit) written back
+// over S in TMEM -> tcgen05.mma (O = P V, A operand from TMEM) -> normalise -> swizzled SMEM -> TMA store.
+// S and P never touch HBM (the reference materialises both: core/sparse_attention.py:84-92).
+//
+// One CTA = one 128-query tile (4 block-rows of the 32x32 layout) of one (batch, head).  The union of key blocks
+// those 4 block-rows attend is a contiguous band of (left+3+nsup) blocks plus the global block 0, i.e. <= 8 "slots"
+// of 32 keys at window 4; all of it fits TMEM at once (128 lanes x 32*slots fp32 columns), so the softmax is a
+// plain two-pass row softmax over the LIVE slots of the warp's block-row -- each of the 4 softmax warps owns
+// exactly one block-row (TMEM lane quarter), so block-level sparsity is warp-uniform and dead blocks cost nothing
+// on the CUDA cores.  TMEM budget: S [0, 32*slots) ; P aliases S in place (in-order overwrite) ; O in a dead
+// part of S.  <= 256 columns -> two CTAs per SM overlap each other's load / MMA / softmax / store phases.
+//
+// Roofline: HBM-bound (AI ~ 79 FLOP/B at window 4, ridge ~ 215): algorithmic bytes = 4 * B*L*H*Dh * 2 per launch.
+#include "attn_sm100.cuh"
+
+namespace svae {
+namespace sm100 {
+
+using namespace ptx;
+
+template <int DH, int NSMAX>
+struct FwdSmem {
+  static constexpr int ROWB = DH * 2;
+  static constexpr int Q_BYTES = kTile * ROWB;
+  static constexpr int SLOT_BYTES = kBlock * ROWB;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + NSMAX * SLOT_BYTES;
+  static constexpr int OFF_KPM = OFF_V + NSMAX * SLOT_BYTES;
+  static constexpr int OFF_BAR = OFF_KPM + NSMAX * kBlock * 4;
+  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024-byte alignment
+  static constexpr int TMEM_COLS = NSMAX <= 8 ? 256 : 512;
+  static constexpr int O_COL = NSMAX <= 8 ? 128 : 448;
+  static_assert(NSMAX * kBlock <= O_COL || NSMAX <= 8, "S must not overlap O when they are both live");
+  static_assert(O_COL + DH <= TMEM_COLS, "O does not fit");
+  static_assert(NSMAX * kBlock / 2 <= O_COL, "P must not overlap O");
+};
+
+template <typename T, int DH, int NSMAX>
+__global__ void __launch_bounds__(kThreads, NSMAX <= 8 ? 2 : 1)
+attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                      const FwdParams p) {
+  using S = FwdSmem<DH, NSMAX>;
+  constexpr int ROWB = S::ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + S::OFF_Q;
+  uint8_t* sK = smem + S::OFF_K;
+  uint8_t* sV = smem + S::OFF_V;
+  float* sKpm = reinterpret_cast<float*>(smem + S::OFF_KPM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* bar_qk = bars + 0;   // TMA: Q + K slots landed
+  uint64_t* bar_v = bars + 1;    // TMA: V slots landed
+  uint64_t* bar_s = bars + 2;    // MMA: S complete in TMEM
+  uint64_t* bar_p = bars + 3;    // softmax: P written to TMEM (128 arrivals)
+  uint64_t* bar_o = bars + 4;    // MMA: O complete in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const TileGeom g = p.g;
+  const int ns = g.nslots;
+  const int r0 = 4 * t;
+  const int band_lo = r0 - (g.left - 1);
+
+  auto slot_block = [&](int j) { return (g.cls && j == 0) ? 0 : band_lo + j - g.cls; };
+  auto slot_valid = [&](int j) {
+    if (g.cls && j == 0) return true;
+    int blk = band_lo + j - g.cls;
+    return blk >= g.cls && blk < g.nb;
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      prefetch_tensormap(&tmQ);
+      prefetch_tensormap(&tmK);
+      prefetch_tensormap(&tmV);
+      prefetch_tensormap(&tmO);
+    }
+    tmem_alloc<S::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================= producer + MMA issuer (one elected lane) =================
+    if (lane == 0) {
+      int nvalid = 0;
+      for (int j = 0; j < ns; ++j) nvalid += slot_valid(j) ? 1 : 0;
+      mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + nvalid * S::SLOT_BYTES);
+      tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
+      for (int j = 0; j < ns; ++j)
+        if (slot_valid(j)) tma_load_4d(sK + j * S::SLOT_BYTES, &tmK, bar_qk, 0, slot_block(j) * kBlock, h, b);
+      mbar_arrive_expect_tx(bar_v, nvalid * S::SLOT_BYTES);
+      for (int j = 0; j < ns; ++j)
+        if (slot_valid(j)) tma_load_4d(sV + j * S::SLOT_BYTES, &tmV, bar_v, 0, slot_block(j) * kBlock, h, b);
+
+      // ---- S = Q K^T : M = 128, N = 32*ns (split at 256), K = DH in steps of 16
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const int ntot = ns * kBlock;
+      for (int n0 = 0; n0 < ntot; n0 += 256) {
+        const int n = (ntot - n0) < 256 ? (ntot - n0) : 256;
+        const uint32_t idesc = make_idesc(kTile, n, Elem<T>::fmt, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint64_t ad = make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB);
+          const uint64_t bd = make_smem_desc(k_addr + n0 * ROWB + ks * 32, 16, 8 * ROWB, ROWB);
+          mma_ss(tmem_base + n0, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      tc_commit(bar_s);
+
+      // ---- O = P V : A = P from TMEM (16-bit, 8 columns per 16 keys), B = V slot (MN-major), N = DH
+      mbar_wait(bar_p, 0);
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
+      uint32_t acc = 0;
+      for (int j = 0; j < ns; ++j) {
+        if (!slot_valid(j)) continue;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const uint64_t bd = make_smem_desc(v_addr + j * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB);
+          mma_ts(tmem_base + S::O_COL, tmem_base + 16 * j + 8 * s, bd, idesc_pv, acc);
+          acc = 1;
+        }
+      }
+      tc_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax + epilogue warps: warp w <-> block-row r0 + w <-> TMEM lanes 32w.. =================
+    const int r = r0 + warp;
+    const int row = warp * 32 + lane;
+    const int qpos = t * kTile + row;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+
+    for (int i = threadIdx.x; i < ns * kBlock; i += 128) {
+      const int j = i >> 5, c = i & 31;
+      float kv = 0.f;
+      if (p.kpm && slot_valid(j)) kv = p.kpm[(int64_t)b * p.L + slot_block(j) * kBlock + c] * kLog2e;
+      sKpm[i] = kv;
+    }
+    named_bar_sync(1, 128);
+
+    auto slot_live = [&](int j) {
+      if (r >= g.nb || !slot_valid(j)) return false;
+      if (g.cls && j == 0) return true;
+      const int blk = band_lo + j - g.cls;
+      return blk >= r - (g.left - 1) && blk <= r + g.nsup;
+    };
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+
+    if (p.s_dump) {   // debug only
+      for (int j = 0; j < ns; ++j) {
+        uint32_t v[32];
+        tmem_ld32(trow + 32 * j, v);
+        tmem_wait_ld();
+        if (qpos < p.L) {
+          float* dst = p.s_dump + (((int64_t)b * p.H + h) * p.L + qpos) * (ns * kBlock) + j * kBlock;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dst[c] = __uint_as_float(v[c]);
+        }
+      }
+    }
+
+    // ---- pass 1: row max over the live slots (log2 domain)
+    float m = -INFINITY;
+    for (int j = 0; j < ns; ++j) {
+      if (!slot_live(j)) continue;
+      uint32_t v[32];
+      tmem_ld32(trow + 32 * j, v);
+      tmem_wait_ld();
+      const bool diag = g.causal && (slot_block(j) == r);
+      const float* kp = sKpm + j * kBlock;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float x = fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]);
+        if (diag && c > lane) x = -INFINITY;
+        m = fmaxf(m, x);
+      }
+    }
+    const float m_safe = (m == -INFINITY) ? 0.f : m;
+
+    // ---- pass 2: P = exp2(x - m) as 16-bit pairs written over S (columns [16j, 16j+16) for slot j), row sum
+    float l = 0.f;
+    for (int j = 0; j < ns; ++j) {
+      uint32_t pk[16];
+      if (slot_live(j)) {
+        uint32_t v[32];
+        tmem_ld32(trow + 32 * j, v);
+        tmem_wait_ld();
+        const bool diag = g.causal && (slot_block(j) == r);
+        const float* kp = sKpm + j * kBlock;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float x0 = fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]);
+          float x1 = fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]);
+          if (diag && c > lane) x0 = -INFINITY;
+          if (diag && c + 1 > lane) x1 = -INFINITY;
+          const float p0 = fast_exp2(x0 - m_safe), p1 = fast_exp2(x1 - m_safe);
+          l += p0 + p1;
+          pk[c >> 1] = Elem<T>::pack(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pk[c] = 0u;
+      }
+      tmem_st16(trow + 16 * j, pk);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    // ---- epilogue: O / l -> 16-bit -> swizzled staging tile (reuses the Q buffer) -> TMA store ; LSE
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
+#pragma unroll
+    for (int half = 0; half < DH / 32; ++half) {
+      uint32_t v[32];
+      tmem_ld32(trow + S::O_COL + 32 * half, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int cq = 0; cq < 4; ++cq) {
+        uint4 w;
+        w.x = Elem<T>::pack(__uint_as_float(v[cq * 8 + 0]) * inv, __uint_as_float(v[cq * 8 + 1]) * inv);
+        w.y = Elem<T>::pack(__uint_as_float(v[cq * 8 + 2]) * inv, __uint_as_float(v[cq * 8 + 3]) * inv);
+        w.z = Elem<T>::pack(__uint_as_float(v[cq * 8 + 4]) * inv, __uint_as_float(v[cq * 8 + 5]) * inv);
+        w.w = Elem<T>::pack(__uint_as_float(v[cq * 8 + 6]) * inv, __uint_as_float(v[cq * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(sQ + swz_off<ROWB>(row, half * 4 + cq)) = w;
+      }
+    }
+    if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 0) {
+      tma_store_4d(&tmO, sQ, 0, t * kTile, h, b);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<S::TMEM_COLS>(tmem_base);
+}
+
+template <typename T, int DH, int NSMAX>
+static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q, const void* k, const void* v,
+                      const float* kpm, void* out, float* lse, float* s_dump, cudaStream_t st) {
+  using S = FwdSmem<DH, NSMAX>;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = encode_tmap(&tmQ, Elem<T>::tm, q, DH, d->seq_len, d->heads, d->batch, d->q_stride, kTile))) return rc;
+  if ((rc = encode_tmap(&tmK, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, kBlock))) return rc;
+  if ((rc = encode_tmap(&tmV, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, kBlock))) return rc;
+  if ((rc = encode_tmap(&tmO, Elem<T>::tm, out, DH, d->seq_len, d->heads, d->batch, d->o_stride, kTile))) return rc;
+  FwdParams p;
+  p.kpm = kpm; p.lse = lse; p.s_dump = s_dump;
+  p.L = d->seq_len; p.H = d->heads; p.g = g;
+  p.scale_log2 = d->scale * kLog2e;
+  auto kern = attn_fwd_sm100_kernel<T, DH, NSMAX>;
+  static bool configured = false;   // benign race: attribute set is idempotent
+  if (!configured) {
+    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+    configured = true;
+  }
+  dim3 grid((d->seq_len + kTile - 1) / kTile, d->heads, d->batch);
+  kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmO, p);
+  SVAE_CUDA_CHECK(cudaGetLastError());
+  return SVAE_OK;
+}
+
+int fwd_max_slots() { return 14; }
+
+int fwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const float* kpm, void* out, float* lse,
+        float* s_dump, cudaStream_t st) {
+  const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
+  SVAE_REQUIRE(g.nslots <= 14, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: %d key slots (window %d) exceed 14",
+               g.nslots, d->window_size);
+  const bool small = g.nslots <= 8;
+#define SVAE_FWD(T, DH)                                                                              \
+  return small ? launch_fwd<T, DH, 8>(d, g, q, k, v, kpm, out, lse, s_dump, st)                      \
+               : launch_fwd<T, DH, 14>(d, g, q, k, v, kpm, out, lse, s_dump, st)
+  if (d->dtype == SVAE_DTYPE_BF16) {
+    if (d->head_dim == 64) { SVAE_FWD(__nv_bfloat16, 64); }
+    if (d->head_dim == 32) { SVAE_FWD(__nv_bfloat16, 32); }
+  } else if (d->dtype == SVAE_DTYPE_F16) {
+    if (d->head_dim == 64) { SVAE_FWD(__half, 64); }
+    if (d->head_dim == 32) { SVAE_FWD(__half, 32); }
+  }
+#undef SVAE_FWD
+  SVAE_REQUIRE(false, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: dtype %d / head_dim %d not supported", d->dtype,
+               d->head_dim);
+}
+
+}  // namespace sm100
+}  // namespace svae

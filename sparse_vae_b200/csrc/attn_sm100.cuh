@@ -1,0 +1,94 @@
+// Shared definitions of the sm_100a (tcgen05 / TMEM / TMA) attention kernels.
+#pragma once
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace svae {
+namespace sm100 {
+
+constexpr int kTile = 128;        // rows of one MMA tile (queries in fwd / dQ, keys in dK/dV) = TMEM lanes
+constexpr int kBlock = 32;        // SparseAttention.block_size
+constexpr int kThreads = 160;     // warps 0-3: softmax / epilogue (one TMEM lane quarter each), warp 4: TMA + MMA issue
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int fmt = 1;
+  static constexpr CUtensorMapDataType tm = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+template <> struct Elem<__half> {
+  static constexpr int fmt = 0;
+  static constexpr CUtensorMapDataType tm = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  __device__ static __forceinline__ uint32_t pack(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Byte offset of 16-byte chunk `chunk` of row `row` inside a TMA-swizzled tile whose rows are ROWB bytes
+// (ROWB = 128 -> SWIZZLE_128B: chunk ^= row & 7;  ROWB = 64 -> SWIZZLE_64B: chunk ^= (row >> 1) & 3).
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz_off(int row, int chunk) {
+  if (ROWB == 128) return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+  return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+// Geometry of one 128-row tile against the banded + global-column layout.
+//   fwd / dQ (query tile t):  slot 0 = key block 0 when cls; slots cls.. = key blocks lo .. lo+nband-1, lo = 4t-(left-1)
+//   dK/dV   (key tile t):     slots 0..nband-1 = query blocks 4t-nsup .. ; (the global column is handled by the dQ pass)
+struct TileGeom {
+  int left, nsup, cls, causal;
+  int nb;          // blocks in the sequence
+  int nband;       // left + 3 + nsup
+  int nslots;      // fwd/dQ: cls + nband ; dK/dV: nband
+};
+
+__host__ __device__ inline TileGeom make_geom(int window, int causal, int include_cls, int nb) {
+  Band b = make_band(window, causal, include_cls);
+  TileGeom g;
+  g.left = b.left; g.nsup = b.nsup; g.cls = b.cls; g.causal = causal ? 1 : 0; g.nb = nb;
+  g.nband = b.left + 3 + b.nsup;
+  g.nslots = g.cls + g.nband;
+  return g;
+}
+
+struct FwdParams {
+  const float* kpm;     // [B, L] additive or null
+  float* lse;           // [B, H, L]
+  float* s_dump;        // debug: [B, H, L, nslots*32] raw scores, or null
+  int L, H;
+  TileGeom g;
+  float scale_log2;     // scale * log2(e)
+};
+
+struct BwdParams {
+  const float* kpm;
+  const float* lse;     // [B, H, L] natural log
+  float* delta;         // [B, H, L] rowsum(dO * O): written by the dQ pass, read by the dK/dV pass
+  float* gacc;          // [B, H, 2, 32, Dh] fp32: dK / dV of key block 0 (global column), atomically accumulated
+  int L, H;
+  TileGeom g;
+  float scale, scale_log2;
+};
+
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int Dh, int L, int H, int B,
+                const int64_t stride[3], int box_rows);
+
+}  // namespace sm100
+}  // namespace svae

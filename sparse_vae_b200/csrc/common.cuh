@@ -1,0 +1,71 @@
+// Shared host/device helpers for libsvae_b200: error plumbing, dtype conversion, block-band geometry.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sparse_vae_b200.h"
+
+namespace svae {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SVAE_CUDA_CHECK(expr)                                         \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) return ::svae::cuda_fail(_e, #expr);       \
+  } while (0)
+
+#define SVAE_REQUIRE(cond, code, ...)                                 \
+  do {                                                                \
+    if (!(cond)) {                                                    \
+      ::svae::set_error(__VA_ARGS__);                                 \
+      return (code);                                                  \
+    }                                                                 \
+  } while (0)
+
+// ---- geometry of the banded + global-column layout -------------------------------------------
+// SparseAttention.get_master_layout (reference core/sparse_attention.py:38-59) only ever produces
+// "band + optional column 0": block-row r attends key blocks [r - (left-1), r + nsup] and block 0.
+struct Band {
+  int left;   // sub-diagonals including the main one  (= left_context)
+  int nsup;   // super-diagonals                        (= max(right_context - 1, 0))
+  int cls;    // column 0 always attended
+};
+
+__host__ __device__ inline Band make_band(int window, int causal, int include_cls) {
+  int sides = causal ? 1 : 2;
+  int left = window / sides + window % sides;
+  int right = window - left;
+  Band b;
+  b.left = left;
+  b.nsup = right > 1 ? right - 1 : 0;
+  b.cls = include_cls ? 1 : 0;
+  return b;
+}
+
+__host__ __device__ inline bool block_live(const Band& g, int r, int c) {
+  if (g.cls && c == 0) return true;
+  return c >= r - (g.left - 1) && c <= r + g.nsup;
+}
+
+// ---- dtype helpers -----------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T x);
+template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+
+inline size_t dtype_size(int dtype) { return dtype == SVAE_DTYPE_F32 ? 4 : 2; }
+
+}  // namespace svae
