@@ -74,6 +74,12 @@ SVAE_API const char* svae_last_error(void);
 /* 0 if the current CUDA device can run the kernels (compute capability 10.x), else SVAE_ERR_DEVICE */
 SVAE_API int svae_device_check(void);
 
+/* ---- measurement: per-kernel device time of every launch the library makes between begin and end, taken
+ * with CUDA events on the launching stream.  svae_profile_end synchronises on the recorded events and writes a
+ * JSON object {"<kernel>": {"launches": n, "ms": total}, ...} into buf. */
+SVAE_API void svae_profile_begin(void);
+SVAE_API int svae_profile_end(char* buf, size_t buf_bytes);
+
 /* ---- layout (host only; bit-exact with get_master_layout()[..., :nb, :nb]) ------------------- */
 /* non-zero blocks per head */
 SVAE_API int64_t svae_layout_nnz(int32_t num_blocks, int32_t window_size, int32_t causal, int32_t include_cls);

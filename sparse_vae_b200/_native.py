@@ -2,7 +2,7 @@
 
 The library is the ONLY implementation of the hot path: if it is missing or cannot be loaded the import of
 this module raises -- there is no Python / CPU fallback.  Build it with
-`python -m sparse_vae_b200.csrc.build` (or `__graft_entry__.build()`).
+`python sparse_vae_b200/csrc/build.py` (or `__graft_entry__.build()`).
 """
 from __future__ import annotations
 
@@ -25,6 +25,7 @@ EXPORTS = (
     'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
+    'svae_profile_begin', 'svae_profile_end',
 )
 
 
@@ -48,7 +49,7 @@ def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: the sparse-vae hot path has no fallback implementation. "
-            f"Build it with `python -m sparse_vae_b200.csrc.build`.")
+            f"Build it with `python sparse_vae_b200/csrc/build.py`.")
     lib = C.CDLL(str(LIB_PATH))
     vp, i32, i64, u64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
     desc_p = C.POINTER(AttnDesc)
@@ -78,6 +79,10 @@ def _load() -> C.CDLL:
     lib.svae_bottleneck_philox_increment.argtypes = [i64, i32, i32, i32]
     lib.svae_bottleneck_bwd.restype = C.c_int
     lib.svae_bottleneck_bwd.argtypes = [vp, i64, i32, vp, i64, i32, u64, u64, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.svae_profile_begin.restype = None
+    lib.svae_profile_begin.argtypes = []
+    lib.svae_profile_end.restype = C.c_int
+    lib.svae_profile_end.argtypes = [C.c_char_p, C.c_size_t]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib
@@ -106,3 +111,15 @@ def ptr(t) -> int:
 
 def current_stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def profile_begin():
+    lib.svae_profile_begin()
+
+
+def profile_end() -> dict:
+    """{kernel name: {'launches': n, 'ms': total device time}} for every library launch since profile_begin()."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.svae_profile_end(buf, len(buf)), 'svae_profile_end')
+    return json.loads(buf.value.decode())

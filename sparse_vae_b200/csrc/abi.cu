@@ -2,6 +2,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace svae {
@@ -20,9 +25,74 @@ int cuda_fail(cudaError_t e, const char* what) {
   return SVAE_ERR_CUDA;
 }
 
+// ---- per-kernel timing ----------------------------------------------------------------------------
+struct ProfRecord {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+
+ScopedKernelTimer::ScopedKernelTimer(const char* name, cudaStream_t s) : slot(-1), st(s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRecord r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+
+ScopedKernelTimer::~ScopedKernelTimer() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, st);
+}
+
 }  // namespace svae
 
 using namespace svae;
+
+extern "C" void svae_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+
+// Stops recording, waits for the recorded events and writes {"kernel": {"launches": n, "ms": total}, ...}.
+extern "C" int svae_profile_end(char* buf, size_t n) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  std::map<std::string, std::pair<long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    out += tmp;
+    first = false;
+  }
+  out += "}";
+  SVAE_REQUIRE(buf && out.size() + 1 <= n, SVAE_ERR_INVALID, "svae_profile_end: buffer of %zu bytes too small (%zu needed)",
+               n, out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return SVAE_OK;
+}
 
 extern "C" int svae_abi_version(void) { return SVAE_ABI_VERSION; }
 

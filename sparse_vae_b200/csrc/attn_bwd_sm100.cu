@@ -550,9 +550,15 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
     configured = true;
   }
   dim3 grid((L + kTile - 1) / kTile, H, B);
-  kq<<<grid, kThreads, DqSmem<DH>::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tDQ128, p);
+  {
+    ScopedKernelTimer timer("attn_bwd_dq_sm100", st);
+    kq<<<grid, kThreads, DqSmem<DH>::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tDQ128, p);
+  }
   SVAE_CUDA_CHECK(cudaGetLastError());
-  kkv<<<grid, kThreads, DkvSmem<DH>::DYN_BYTES, st>>>(tK128, tV128, tQ32, tDO32, tDK128, tDV128, p);
+  {
+    ScopedKernelTimer timer("attn_bwd_dkv_sm100", st);
+    kkv<<<grid, kThreads, DkvSmem<DH>::DYN_BYTES, st>>>(tK128, tV128, tQ32, tDO32, tDK128, tDV128, p);
+  }
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }

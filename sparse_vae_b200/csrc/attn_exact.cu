@@ -280,6 +280,7 @@ static void fill_args(ExactArgs& a, const svae_attn_desc* d) {
 template <typename T>
 static int launch_fwd_t(const ExactArgs& a, cudaStream_t st) {
   dim3 grid(a.nb, a.H, a.B);
+  ScopedKernelTimer timer("attn_exact_fwd", st);
   switch (a.Dh) {
     case 16: attn_exact_fwd_kernel<T, 16><<<grid, kExThreads, 0, st>>>(a); break;
     case 32: attn_exact_fwd_kernel<T, 32><<<grid, kExThreads, 0, st>>>(a); break;
@@ -295,6 +296,7 @@ static int launch_bwd_t(const ExactArgs& a, const svae_attn_desc* d, void* dk, v
   dim3 grid(a.nb, a.H, a.B);
   const int64_t total = (int64_t)a.B * a.H * a.L * a.Dh;
   SVAE_CUDA_CHECK(cudaMemsetAsync(a.dk_acc, 0, sizeof(float) * total * 2, st));   // dk_acc and dv_acc are adjacent
+  ScopedKernelTimer timer("attn_exact_bwd", st);
   switch (a.Dh) {
     case 16: attn_exact_bwd_kernel<T, 16><<<grid, kExThreads, 0, st>>>(a); break;
     case 32: attn_exact_bwd_kernel<T, 32><<<grid, kExThreads, 0, st>>>(a); break;

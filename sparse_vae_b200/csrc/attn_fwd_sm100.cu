@@ -284,6 +284,7 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
     configured = true;
   }
   dim3 grid((d->seq_len + kTile - 1) / kTile, d->heads, d->batch);
+  ScopedKernelTimer timer("attn_fwd_sm100", st);
   kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmO, p);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;

@@ -305,6 +305,7 @@ extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dty
   BnFwdArgs a{mulogvar, ld, token_counts, rows, latent, p.pp, z, sigma, kl_elem, raw_kl, kl,
               reinterpret_cast<float*>(workspace), p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScopedKernelTimer timer("bottleneck_fwd", st);
 #define SVAE_BN_LAUNCH(T)                                                              \
   do {                                                                                 \
     if (p.share) bottleneck_fwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a);     \
@@ -335,6 +336,7 @@ extern "C" int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dty
   BnBwdArgs a{mulogvar, ld, token_counts, rows, latent, p.pp, dz, dsigma, dkl_elem, draw_kl, dkl, d_mulogvar, ld_out,
               p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ScopedKernelTimer timer("bottleneck_bwd", st);
 #define SVAE_BN_LAUNCH(T)                                                              \
   do {                                                                                 \
     if (p.share) bottleneck_bwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a);     \

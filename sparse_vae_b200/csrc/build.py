@@ -1,6 +1,6 @@
 """Builds libsvae_b200.so (the C-ABI library of include/sparse_vae_b200.h) in-tree with nvcc for sm_100a.
 
-    python -m sparse_vae_b200.csrc.build [--force] [--verbose]
+    python sparse_vae_b200/csrc/build.py [--force] [--verbose]
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
 """
@@ -39,7 +39,7 @@ def _stamp() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
-    stamp_file = BUILD / 'stamp'
+    stamp_file = HERE / 'libsvae_b200.stamp'      # travels with the .so (build/ does not)
     stamp = _stamp()
     if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB

@@ -30,6 +30,15 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                                                 \
   } while (0)
 
+// ---- optional per-kernel device timing (svae_profile_begin / svae_profile_end) ---------------------
+// When enabled, every kernel launch of the library is bracketed by two CUDA events on its own stream.
+struct ScopedKernelTimer {
+  ScopedKernelTimer(const char* name, cudaStream_t st);
+  ~ScopedKernelTimer();
+  int slot;
+  cudaStream_t st;
+};
+
 // ---- geometry of the banded + global-column layout -------------------------------------------
 // SparseAttention.get_master_layout (reference core/sparse_attention.py:38-59) only ever produces
 // "band + optional column 0": block-row r attends key blocks [r - (left-1), r + nsup] and block 0.
