@@ -155,3 +155,56 @@ def training_step(p: Dict[str, torch.Tensor], token_ids: torch.Tensor, num_token
     nll = F.cross_entropy(logits.flatten(end_dim=1), original[..., 1:].flatten(), ignore_index=0)
     loss = nll + kl_weight * kl
     return dict(loss=loss, nll=nll, kl=kl, raw_kl=raw_kl, z=z, mu=mu, logvar=logvar)
+
+
+def init_params(d_model: int = 512, num_layers: int = 6, latent: int = 64, vocab: int = 2 ** 15,
+                init_scale: float = 0.02, seed: int = 7295) -> Dict[str, torch.Tensor]:
+    """Random-init parameter dict with the reference's names and shapes (transformer_vae.py:26-40,
+    core/transformer_language_model.py:34-72, core/perceiver.py:8-28) and its BERT-style init
+    (core/language_model.py:80-96): N(0, init_scale) weights, zero biases, LayerNorm at identity,
+    learned queries ~ N(0, 1)."""
+    g = torch.Generator().manual_seed(seed)
+    p: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_f, in_f, bias=True):
+        p[name + '.weight'] = torch.randn(out_f, in_f, generator=g) * init_scale
+        if bias:
+            p[name + '.bias'] = torch.zeros(out_f)
+
+    def ln(name):
+        p[name + '.weight'] = torch.ones(d_model)
+        p[name + '.bias'] = torch.zeros(d_model)
+
+    def attn(name, learned=0):
+        if learned:
+            p[name + '.learned_queries'] = torch.randn(1, learned, d_model, generator=g)
+        else:
+            lin(name + '.q_linear', d_model, d_model)
+        for nm in ('k_linear', 'v_linear', 'output_linear', 'pos_linear'):
+            lin(f'{name}.{nm}', d_model, d_model)
+
+    def layer(name, learned=0, cross=False):
+        attn(name + '.attention', learned)
+        lin(name + '.ffn.0', 4 * d_model, d_model)
+        lin(name + '.ffn.2', d_model, 4 * d_model, bias=False)
+        ln(name + '.attn_layer_norm')
+        ln(name + '.ffn_layer_norm')
+        if cross:
+            attn(name + '.cross_attention')
+            ln(name + '.cross_attn_layer_norm')
+            ln(name + '.context_layer_norm')
+
+    p['input_layer.0.weight'] = torch.randn(vocab, d_model, generator=g) * init_scale
+    lin('output_layer.0', d_model, d_model)
+    ln('output_layer.2')
+    p['output_layer.3.bias'] = torch.zeros(vocab)
+    for i in range(num_layers):
+        layer(f'decoder_layers.{i}')
+        lin(f'z_projections.{i}', d_model, latent)
+    lin('q_of_z_given_x.linear', 2 * latent, d_model)
+    enc_layers = num_layers // 2
+    layer('encoder.first_layer', learned=64)
+    layer('encoder.bottleneck', learned=1)
+    for i in range(enc_layers - 2):
+        layer(f'encoder.middle_layers.{i}', cross=True)
+    return {k: v.requires_grad_(True) for k, v in p.items()}
