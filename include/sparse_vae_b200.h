@@ -104,12 +104,19 @@ SVAE_API int svae_attn_bwd(const svae_attn_desc* desc, const void* q, const void
                   const void* out, const void* dout, const float* lse, const float* key_padding_mask,
                   void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Debug variant of svae_attn_fwd for the tcgen05 path: additionally dumps the raw scores
- * S = q k^T (before scale/masks) of every query row against its tile's key slots to
- * s_dump[batch, heads, seq_len, slots*32] (fp32; slots = svae_attn_fwd_slots(desc)). */
+/* Debug variant of svae_attn_fwd for the tcgen05 path.  s_dump (may be NULL): raw scores S = q k^T (before
+ * scale/masks) of every query row against its tile's key slots, [batch, heads, seq_len, slots*32] fp32
+ * (slots = svae_attn_fwd_slots(desc)).  timeline (may be NULL): int64 [num_ctas, 5, 8] per-warp clock64
+ * stamps of the kernel's phases (CTA order: batch, head, tile). */
 SVAE_API int svae_attn_fwd_slots(const svae_attn_desc* desc);
 SVAE_API int svae_attn_fwd_debug(const svae_attn_desc* desc, const void* q, const void* k, const void* v,
-                        const float* key_padding_mask, void* out, float* lse, float* s_dump, void* stream);
+                        const float* key_padding_mask, void* out, float* lse, float* s_dump,
+                        long long* timeline, void* stream);
+
+/* Debug micro-benchmark (one CTA): clock64 cycles to issue `count` back-to-back tcgen05.mma (M=128, K=16, N=n).
+ * variant bit 0: A from TMEM, bit 1: B MN-major, bit 2: two issuing warps.  out: int64[4] =
+ * {issue, issue+drain} per issuing warp. */
+SVAE_API int svae_debug_mma_bench(int variant, int n, int count, long long* out, void* stream);
 
 /* ---- latent bottleneck ---------------------------------------------------------------------- */
 #define SVAE_BOTTLENECK_WORKSPACE_BYTES 8448

@@ -25,7 +25,7 @@ EXPORTS = (
     'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
-    'svae_profile_begin', 'svae_profile_end',
+    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench',
 )
 
 
@@ -66,7 +66,7 @@ def _load() -> C.CDLL:
     lib.svae_attn_fwd.restype = C.c_int
     lib.svae_attn_fwd.argtypes = [desc_p, vp, vp, vp, f32p, vp, f32p, vp]
     lib.svae_attn_fwd_debug.restype = C.c_int
-    lib.svae_attn_fwd_debug.argtypes = [desc_p, vp, vp, vp, f32p, vp, f32p, f32p, vp]
+    lib.svae_attn_fwd_debug.argtypes = [desc_p, vp, vp, vp, f32p, vp, f32p, f32p, vp, vp]
     lib.svae_attn_fwd_slots.restype = C.c_int
     lib.svae_attn_fwd_slots.argtypes = [desc_p]
     lib.svae_attn_bwd_workspace_bytes.restype = C.c_size_t
@@ -83,6 +83,8 @@ def _load() -> C.CDLL:
     lib.svae_profile_begin.argtypes = []
     lib.svae_profile_end.restype = C.c_int
     lib.svae_profile_end.argtypes = [C.c_char_p, C.c_size_t]
+    lib.svae_debug_mma_bench.restype = C.c_int
+    lib.svae_debug_mma_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib

@@ -14,7 +14,7 @@ int exact_bwd(const svae_attn_desc*, const void*, const void*, const void*, cons
 
 namespace sm100 {
 
-int fwd(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, float*, cudaStream_t);
+int fwd(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, float*, long long*, cudaStream_t);
 size_t bwd_workspace(const svae_attn_desc*);
 bool bwd_supported(const svae_attn_desc*);
 int bwd(const svae_attn_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
@@ -100,7 +100,7 @@ extern "C" int svae_attn_fwd_slots(const svae_attn_desc* d) {
 }
 
 static int attn_fwd_impl(const svae_attn_desc* d, const void* q, const void* k, const void* v, const float* kpm,
-                         void* out, float* lse, float* s_dump, void* stream) {
+                         void* out, float* lse, float* s_dump, long long* timeline, void* stream) {
   int rc = validate(d, false);
   if (rc) return rc;
   SVAE_REQUIRE(q && k && v && out && lse, SVAE_ERR_INVALID, "svae_attn_fwd: null tensor pointer");
@@ -112,17 +112,18 @@ static int attn_fwd_impl(const svae_attn_desc* d, const void* q, const void* k, 
   SVAE_REQUIRE(tma_ok(q, d->q_stride, d->heads, d->batch, d->seq_len) && tma_ok(k, d->k_stride, d->heads, d->batch, d->seq_len) &&
                    tma_ok(v, d->v_stride, d->heads, d->batch, d->seq_len) && tma_ok(out, d->o_stride, d->heads, d->batch, d->seq_len),
                SVAE_ERR_INVALID, "svae_attn_fwd: 16-bit tensors must be 16-byte aligned with strides that are multiples of 8 elements");
-  return sm100::fwd(d, q, k, v, kpm, out, lse, s_dump, st);
+  return sm100::fwd(d, q, k, v, kpm, out, lse, s_dump, timeline, st);
 }
 
 extern "C" int svae_attn_fwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const float* kpm,
                              void* out, float* lse, void* stream) {
-  return attn_fwd_impl(d, q, k, v, kpm, out, lse, nullptr, stream);
+  return attn_fwd_impl(d, q, k, v, kpm, out, lse, nullptr, nullptr, stream);
 }
 
 extern "C" int svae_attn_fwd_debug(const svae_attn_desc* d, const void* q, const void* k, const void* v,
-                                   const float* kpm, void* out, float* lse, float* s_dump, void* stream) {
-  return attn_fwd_impl(d, q, k, v, kpm, out, lse, s_dump, stream);
+                                   const float* kpm, void* out, float* lse, float* s_dump, long long* timeline,
+                                   void* stream) {
+  return attn_fwd_impl(d, q, k, v, kpm, out, lse, s_dump, timeline, stream);
 }
 
 extern "C" size_t svae_attn_bwd_workspace_bytes(const svae_attn_desc* d) {

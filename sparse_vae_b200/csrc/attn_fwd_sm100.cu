@@ -10,6 +10,7 @@
 // exactly one block-row (TMEM lane quarter), so block-level sparsity is warp-uniform and dead blocks cost nothing
 // on the CUDA cores.  TMEM budget: S [0, 32*slots) ; P aliases S in place (in-order overwrite) ; O in a dead
 // part of S.  <= 256 columns -> two CTAs per SM overlap each other's load / MMA / softmax / store phases.
+// The whole band arrives with ONE TMA box per operand (rows outside [0, L) are zero-filled by the TMA unit).
 //
 // Roofline: HBM-bound (AI ~ 79 FLOP/B at window 4, ridge ~ 215): algorithmic bytes = 4 * B*L*H*Dh * 2 per launch.
 #include "attn_sm100.cuh"
@@ -38,13 +39,28 @@ struct FwdSmem {
   static_assert(NSMAX * kBlock / 2 <= O_COL, "P must not overlap O");
 };
 
+// max over one 32-column slot of raw scores (4 independent chains, 3-input max)
+__device__ __forceinline__ float slot_max_raw(const uint32_t (&v)[32], float m) {
+  float a = m, b = -INFINITY, c = -INFINITY, d = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    a = fmax3(a, __uint_as_float(v[i + 0]), __uint_as_float(v[i + 1]));
+    b = fmax3(b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    c = fmax3(c, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+    d = fmax3(d, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+  }
+  return fmax3(fmaxf(a, b), c, d);
+}
+
 template <typename T, int DH, int NSMAX>
 __global__ void __launch_bounds__(kThreads, NSMAX <= 8 ? 2 : 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKband,
+                      const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmO,
                       const FwdParams p) {
   using S = FwdSmem<DH, NSMAX>;
   constexpr int ROWB = S::ROWB;
+  constexpr bool kBandTma = NSMAX <= 8;     // the band (<= 8 slots = 256 rows) fits one TMA box
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + S::OFF_Q;
@@ -65,8 +81,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int ns = g.nslots;
   const int r0 = 4 * t;
   const int band_lo = r0 - (g.left - 1);
+  long long* tl = nullptr;
+  if (p.timeline && lane == 0)
+    tl = p.timeline + ((((int64_t)b * gridDim.y + h) * gridDim.x + t) * 5 + warp) * 8;
+  auto stamp = [&](int k) { if (tl) tl[k] = clock64(); };
+  stamp(0);
 
   auto slot_block = [&](int j) { return (g.cls && j == 0) ? 0 : band_lo + j - g.cls; };
+  // a slot carries keys the tile may attend: inside the sequence and not a duplicate of the global block
   auto slot_valid = [&](int j) {
     if (g.cls && j == 0) return true;
     int blk = band_lo + j - g.cls;
@@ -86,6 +108,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       prefetch_tensormap(&tmQ);
       prefetch_tensormap(&tmK);
       prefetch_tensormap(&tmV);
+      prefetch_tensormap(&tmKband);
+      prefetch_tensormap(&tmVband);
       prefetch_tensormap(&tmO);
     }
     tmem_alloc<S::TMEM_COLS>(tmem_slot);
@@ -94,23 +118,37 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  stamp(1);
 
   if (warp == 4) {
     // ================= producer + MMA issuer (one elected lane) =================
     if (lane == 0) {
-      int nvalid = 0;
-      for (int j = 0; j < ns; ++j) nvalid += slot_valid(j) ? 1 : 0;
-      mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + nvalid * S::SLOT_BYTES);
-      tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
-      for (int j = 0; j < ns; ++j)
-        if (slot_valid(j)) tma_load_4d(sK + j * S::SLOT_BYTES, &tmK, bar_qk, 0, slot_block(j) * kBlock, h, b);
-      mbar_arrive_expect_tx(bar_v, nvalid * S::SLOT_BYTES);
-      for (int j = 0; j < ns; ++j)
-        if (slot_valid(j)) tma_load_4d(sV + j * S::SLOT_BYTES, &tmV, bar_v, 0, slot_block(j) * kBlock, h, b);
+      if (kBandTma) {
+        // one box for the whole band; rows < 0 or >= L come back as zeros, so every slot holds finite data
+        mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + ns * S::SLOT_BYTES);
+        tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
+        tma_load_4d(sK + g.cls * S::SLOT_BYTES, &tmKband, bar_qk, 0, band_lo * kBlock, h, b);
+        if (g.cls) tma_load_4d(sK, &tmK, bar_qk, 0, 0, h, b);
+        mbar_arrive_expect_tx(bar_v, ns * S::SLOT_BYTES);
+        tma_load_4d(sV + g.cls * S::SLOT_BYTES, &tmVband, bar_v, 0, band_lo * kBlock, h, b);
+        if (g.cls) tma_load_4d(sV, &tmV, bar_v, 0, 0, h, b);
+      } else {
+        int nvalid = 0;
+        for (int j = 0; j < ns; ++j) nvalid += slot_valid(j) ? 1 : 0;
+        mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + nvalid * S::SLOT_BYTES);
+        tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
+        for (int j = 0; j < ns; ++j)
+          if (slot_valid(j)) tma_load_4d(sK + j * S::SLOT_BYTES, &tmK, bar_qk, 0, slot_block(j) * kBlock, h, b);
+        mbar_arrive_expect_tx(bar_v, nvalid * S::SLOT_BYTES);
+        for (int j = 0; j < ns; ++j)
+          if (slot_valid(j)) tma_load_4d(sV + j * S::SLOT_BYTES, &tmV, bar_v, 0, slot_block(j) * kBlock, h, b);
+      }
 
+      stamp(2);
       // ---- S = Q K^T : M = 128, N = 32*ns (split at 256), K = DH in steps of 16
       mbar_wait(bar_qk, 0);
       tc_fence_after();
+      stamp(3);
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const int ntot = ns * kBlock;
       for (int n0 = 0; n0 < ntot; n0 += 256) {
@@ -124,11 +162,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       tc_commit(bar_s);
+      stamp(4);
 
       // ---- O = P V : A = P from TMEM (16-bit, 8 columns per 16 keys), B = V slot (MN-major), N = DH
       mbar_wait(bar_p, 0);
       mbar_wait(bar_v, 0);
       tc_fence_after();
+      stamp(5);
       const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
       uint32_t acc = 0;
       for (int j = 0; j < ns; ++j) {
@@ -141,6 +181,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       tc_commit(bar_o);
+      stamp(6);
+      if (tl) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tl[7] = (long long)((gt << 8) | (smid & 255)); }
     }
     __syncwarp();
   } else {
@@ -150,13 +192,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int qpos = t * kTile + row;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-    for (int i = threadIdx.x; i < ns * kBlock; i += 128) {
-      const int j = i >> 5, c = i & 31;
-      float kv = 0.f;
-      if (p.kpm && slot_valid(j)) kv = p.kpm[(int64_t)b * p.L + slot_block(j) * kBlock + c] * kLog2e;
-      sKpm[i] = kv;
+    // stage the additive key-padding mask (log2 domain); tiles whose keys are all unmasked take the fast path
+    uint32_t any_kpm = 0;
+    if (p.kpm) {
+      for (int i = threadIdx.x; i < ns * kBlock; i += 128) {
+        const int j = i >> 5, c = i & 31;
+        float kv = 0.f;
+        if (slot_valid(j)) kv = p.kpm[(int64_t)b * p.L + slot_block(j) * kBlock + c] * kLog2e;
+        sKpm[i] = kv;
+        any_kpm |= (kv != 0.f) ? 1u : 0u;
+      }
     }
-    named_bar_sync(1, 128);
+    const bool has_kpm = bar_red_or(1, 128, any_kpm);
 
     auto slot_live = [&](int j) {
       if (r >= g.nb || !slot_valid(j)) return false;
@@ -164,15 +211,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int blk = band_lo + j - g.cls;
       return blk >= r - (g.left - 1) && blk <= r + g.nsup;
     };
+    const uint32_t below_diag = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);   // bit c set <=> key c <= query lane
 
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    stamp(2);
 
     if (p.s_dump) {   // debug only
       for (int j = 0; j < ns; ++j) {
         uint32_t v[32];
         tmem_ld32(trow + 32 * j, v);
-        tmem_wait_ld();
+        tmem_wait_ld(v);
         if (qpos < p.L) {
           float* dst = p.s_dump + (((int64_t)b * p.H + h) * p.L + qpos) * (ns * kBlock) + j * kBlock;
 #pragma unroll
@@ -181,43 +230,69 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
 
-    // ---- pass 1: row max over the live slots (log2 domain)
-    float m = -INFINITY;
+    // ---- pass 1: row max over the live slots
+    float m = -INFINITY;                    // fast path: max of raw scores ; slow path: log2-domain max
     for (int j = 0; j < ns; ++j) {
       if (!slot_live(j)) continue;
       uint32_t v[32];
       tmem_ld32(trow + 32 * j, v);
-      tmem_wait_ld();
+      tmem_wait_ld(v);
       const bool diag = g.causal && (slot_block(j) == r);
-      const float* kp = sKpm + j * kBlock;
+      if (diag) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float x = fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]);
-        if (diag && c > lane) x = -INFINITY;
-        m = fmaxf(m, x);
+        for (int c = 0; c < 32; ++c)
+          if (!((below_diag >> c) & 1u)) v[c] = 0xff800000u;      // -inf
+      }
+      if (!has_kpm) {
+        m = slot_max_raw(v, m);
+      } else {
+        const float* kp = sKpm + j * kBlock;
+        float a0 = m, a1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          a0 = fmaxf(a0, fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]));
+          a1 = fmaxf(a1, fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]));
+        }
+        m = fmaxf(a0, a1);
       }
     }
-    const float m_safe = (m == -INFINITY) ? 0.f : m;
+    if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
+    stamp(3);
+    const float neg_m = (m == -INFINITY) ? 0.f : -m;
 
     // ---- pass 2: P = exp2(x - m) as 16-bit pairs written over S (columns [16j, 16j+16) for slot j), row sum
-    float l = 0.f;
+    float l0 = 0.f, l1 = 0.f;
     for (int j = 0; j < ns; ++j) {
       uint32_t pk[16];
       if (slot_live(j)) {
         uint32_t v[32];
         tmem_ld32(trow + 32 * j, v);
-        tmem_wait_ld();
+        tmem_wait_ld(v);
         const bool diag = g.causal && (slot_block(j) == r);
-        const float* kp = sKpm + j * kBlock;
+        if (diag) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float x0 = fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]);
-          float x1 = fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]);
-          if (diag && c > lane) x0 = -INFINITY;
-          if (diag && c + 1 > lane) x1 = -INFINITY;
-          const float p0 = fast_exp2(x0 - m_safe), p1 = fast_exp2(x1 - m_safe);
-          l += p0 + p1;
-          pk[c >> 1] = Elem<T>::pack(p0, p1);
+          for (int c = 0; c < 32; ++c)
+            if (!((below_diag >> c) & 1u)) v[c] = 0xff800000u;
+        }
+        if (!has_kpm) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), p.scale_log2, neg_m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), p.scale_log2, neg_m));
+            l0 += p0;
+            l1 += p1;
+            pk[c >> 1] = Elem<T>::pack(p0, p1);
+          }
+        } else {
+          const float* kp = sKpm + j * kBlock;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]) + neg_m);
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]) + neg_m);
+            l0 += p0;
+            l1 += p1;
+            pk[c >> 1] = Elem<T>::pack(p0, p1);
+          }
         }
       } else {
 #pragma unroll
@@ -225,19 +300,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       tmem_st16(trow + 16 * j, pk);
     }
+    const float l = l0 + l1;
     tmem_wait_st();
     tc_fence_before();
     mbar_arrive(bar_p);
+    stamp(4);
 
     // ---- epilogue: O / l -> 16-bit -> swizzled staging tile (reuses the Q buffer) -> TMA store ; LSE
+    if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
+    const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
+    stamp(5);
 #pragma unroll
     for (int half = 0; half < DH / 32; ++half) {
       uint32_t v[32];
       tmem_ld32(trow + S::O_COL + 32 * half, v);
-      tmem_wait_ld();
+      tmem_wait_ld(v);
 #pragma unroll
       for (int cq = 0; cq < 4; ++cq) {
         uint4 w;
@@ -248,7 +327,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         *reinterpret_cast<uint4*>(sQ + swz_off<ROWB>(row, half * 4 + cq)) = w;
       }
     }
-    if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
     fence_proxy_async();
     named_bar_sync(1, 128);
     if (threadIdx.x == 0) {
@@ -256,6 +334,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tma_store_commit();
       tma_store_wait_read();
     }
+    stamp(6);
   }
 
   tc_fence_before();
@@ -265,16 +344,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 template <typename T, int DH, int NSMAX>
 static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q, const void* k, const void* v,
-                      const float* kpm, void* out, float* lse, float* s_dump, cudaStream_t st) {
+                      const float* kpm, void* out, float* lse, float* s_dump, long long* timeline, cudaStream_t st) {
   using S = FwdSmem<DH, NSMAX>;
-  CUtensorMap tmQ, tmK, tmV, tmO;
+  CUtensorMap tmQ, tmK, tmV, tmKb, tmVb, tmO;
   int rc;
+  const int band_rows = (g.nband <= 8 ? g.nband : 8) * kBlock;
   if ((rc = encode_tmap(&tmQ, Elem<T>::tm, q, DH, d->seq_len, d->heads, d->batch, d->q_stride, kTile))) return rc;
   if ((rc = encode_tmap(&tmK, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, kBlock))) return rc;
   if ((rc = encode_tmap(&tmV, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, kBlock))) return rc;
+  if ((rc = encode_tmap(&tmKb, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, band_rows))) return rc;
+  if ((rc = encode_tmap(&tmVb, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, band_rows))) return rc;
   if ((rc = encode_tmap(&tmO, Elem<T>::tm, out, DH, d->seq_len, d->heads, d->batch, d->o_stride, kTile))) return rc;
   FwdParams p;
-  p.kpm = kpm; p.lse = lse; p.s_dump = s_dump;
+  p.kpm = kpm; p.lse = lse; p.s_dump = s_dump; p.timeline = timeline;
   p.L = d->seq_len; p.H = d->heads; p.g = g;
   p.scale_log2 = d->scale * kLog2e;
   auto kern = attn_fwd_sm100_kernel<T, DH, NSMAX>;
@@ -285,7 +367,7 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
   }
   dim3 grid((d->seq_len + kTile - 1) / kTile, d->heads, d->batch);
   ScopedKernelTimer timer("attn_fwd_sm100", st);
-  kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmO, p);
+  kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmKb, tmVb, tmO, p);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
@@ -293,14 +375,15 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
 int fwd_max_slots() { return 14; }
 
 int fwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const float* kpm, void* out, float* lse,
-        float* s_dump, cudaStream_t st) {
+        float* s_dump, long long* timeline, cudaStream_t st) {
   const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
   SVAE_REQUIRE(g.nslots <= 14, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: %d key slots (window %d) exceed 14",
                g.nslots, d->window_size);
+  SVAE_REQUIRE(d->scale > 0.f, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: softmax scale must be positive");
   const bool small = g.nslots <= 8;
 #define SVAE_FWD(T, DH)                                                                              \
-  return small ? launch_fwd<T, DH, 8>(d, g, q, k, v, kpm, out, lse, s_dump, st)                      \
-               : launch_fwd<T, DH, 14>(d, g, q, k, v, kpm, out, lse, s_dump, st)
+  return small ? launch_fwd<T, DH, 8>(d, g, q, k, v, kpm, out, lse, s_dump, timeline, st)                      \
+               : launch_fwd<T, DH, 14>(d, g, q, k, v, kpm, out, lse, s_dump, timeline, st)
   if (d->dtype == SVAE_DTYPE_BF16) {
     if (d->head_dim == 64) { SVAE_FWD(__nv_bfloat16, 64); }
     if (d->head_dim == 32) { SVAE_FWD(__nv_bfloat16, 32); }

@@ -72,6 +72,7 @@ struct FwdParams {
   const float* kpm;     // [B, L] additive or null
   float* lse;           // [B, H, L]
   float* s_dump;        // debug: [B, H, L, nslots*32] raw scores, or null
+  long long* timeline;  // debug: [num_ctas, 5 warps, 8] clock64 stamps, or null
   int L, H;
   TileGeom g;
   float scale_log2;     // scale * log2(e)

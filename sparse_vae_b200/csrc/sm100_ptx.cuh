@@ -163,6 +163,36 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fmt, int a_m
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Ties the registers of a preceding tcgen05.ld to the wait, so no use of them can be scheduled above it.
+#define SVAE_DEP8(r, o) "+r"(r[o]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SVAE_DEP8(r, 0), SVAE_DEP8(r, 8) : : "memory");
+  asm volatile("" : SVAE_DEP8(r, 16), SVAE_DEP8(r, 24) : : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SVAE_DEP8(a, 0), SVAE_DEP8(a, 8) : : "memory");
+  asm volatile("" : SVAE_DEP8(a, 16), SVAE_DEP8(a, 24) : : "memory");
+  asm volatile("" : SVAE_DEP8(b, 0), SVAE_DEP8(b, 8) : : "memory");
+  asm volatile("" : SVAE_DEP8(b, 16), SVAE_DEP8(b, 24) : : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// barrier among `nthreads` threads of named barrier `id` that also ORs a predicate across them
+__device__ __forceinline__ bool bar_red_or(int id, int nthreads, uint32_t pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"(pred)
+      : "memory");
+  return out != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -1,0 +1,21 @@
+"""tcgen05.mma issue-cost micro-benchmark (debug entry point svae_debug_mma_bench)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from sparse_vae_b200 import _native as N  # noqa: E402
+
+out = torch.zeros(4, dtype=torch.int64, device='cuda')
+count = 64
+print(f'{count} back-to-back MMAs, M=128 K=16: cycles per MMA (issue | issue+drain)')
+for variant, name in ((0, 'SS K-major B'), (2, 'SS MN-major B'), (1, 'TS K-major B'), (3, 'TS MN-major B'),
+                      (4, 'SS, two warps'), (7, 'TS MN, two warps')):
+    for n in (32, 64, 96, 128, 256):
+        for _ in range(2):
+            out.zero_()
+            N.check(N.lib.svae_debug_mma_bench(variant, n, count, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
+            torch.cuda.synchronize()
+        o = out.tolist()
+        print(f'  {name:18s} N={n:3d}: warp0 {o[0] / count:7.1f} | {o[1] / count:7.1f}   warp1 {o[2] / count:7.1f} | {o[3] / count:7.1f}')

@@ -128,7 +128,7 @@ def test_sm100_raw_scores_dump():
     assert ns == 8
     dump = torch.zeros(B, H, L, ns * 32, device=dev)
     N.check(N.lib.svae_attn_fwd_debug(ctypes.byref(desc), q.data_ptr(), k.data_ptr(), v.data_ptr(), None, out.data_ptr(),
-                                      lse.data_ptr(), dump.data_ptr(), torch.cuda.current_stream().cuda_stream), 'dbg')
+                                      lse.data_ptr(), dump.data_ptr(), None, torch.cuda.current_stream().cuda_stream), 'dbg')
     torch.cuda.synchronize()
     full = (q.float() @ k.float().transpose(-1, -2)).cpu()            # [B,H,L,L]
     dump = dump.cpu()
