@@ -51,6 +51,7 @@ extern "C" {
 
 /* svae_attn_desc.flags */
 #define SVAE_ATTN_FORCE_EXACT  1   /* run 16-bit inputs through the exact CUDA-core path (cross-check / debugging) */
+#define SVAE_ATTN_PERSISTENT   2   /* forward: use the persistent warp-specialised kernel (experimental; default = one CTA per tile) */
 
 /* Block-sparse attention problem.  Tensors are [batch, heads, seq_len, head_dim] with arbitrary
  * batch/head/row strides (in ELEMENTS) and unit inner stride -- the reference hands the op strided

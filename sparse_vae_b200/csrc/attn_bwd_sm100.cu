@@ -67,19 +67,21 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* bar_ds = bars + 5;                              // [3] threads -> MMA: chunk's dS is in TMEM (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const TileGeom g = p.g;
   const int ns = g.nslots;
   const int npass = (ns + PASS - 1) / PASS;
   const int r0 = 4 * t;
   const int band_lo = r0 - (g.left - 1);
-  // processing order: band slots first, the global slot (SMEM slot 0) last
-  auto order = [&](int i) { return i < g.nband ? g.cls + i : 0; };
-  auto slot_block = [&](int j) { return (g.cls && j == 0) ? 0 : band_lo + j - g.cls; };
+  // SMEM slot order = processing order: band slots 0 .. nband-1, then the global block (slot nband), so that the
+  // slots of a chunk are contiguous and one N = 96 MMA chain covers them
+  auto order = [&](int i) { return i; };
+  auto is_global = [&](int j) { return g.cls && j == g.nband; };
+  auto slot_block = [&](int j) { return is_global(j) ? 0 : band_lo + j; };
   auto slot_valid = [&](int j) {
-    if (g.cls && j == 0) return true;
-    int blk = band_lo + j - g.cls;
+    if (is_global(j)) return true;
+    int blk = band_lo + j;
     return blk >= g.cls && blk < g.nb;
   };
 
@@ -103,40 +105,38 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_ld, 3 * S::TILE_BYTES + 2 * ns * S::SLOT_BYTES);
-      tma_load_4d(sQ, &tmQ, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d(sDO, &tmDO, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d(sO, &tmO, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d(sK + g.cls * S::SLOT_BYTES, &tmKband, bar_ld, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
-      tma_load_4d(sV + g.cls * S::SLOT_BYTES, &tmVband, bar_ld, 0, band_lo * kBlock, h, b);
+    {   // the whole warp runs the issue path convergently; one lane is elected inside each wrapper
+      mbar_arrive_expect_tx_w(bar_ld, 3 * S::TILE_BYTES + 2 * ns * S::SLOT_BYTES);
+      tma_load_4d_w(sQ, &tmQ, bar_ld, 0, t * kTile, h, b);
+      tma_load_4d_w(sDO, &tmDO, bar_ld, 0, t * kTile, h, b);
+      tma_load_4d_w(sO, &tmO, bar_ld, 0, t * kTile, h, b);
+      tma_load_4d_w(sK, &tmKband, bar_ld, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
+      tma_load_4d_w(sV, &tmVband, bar_ld, 0, band_lo * kBlock, h, b);
       if (g.cls) {
-        tma_load_4d(sK, &tmK, bar_ld, 0, 0, h, b);
-        tma_load_4d(sV, &tmV, bar_ld, 0, 0, h, b);
+        tma_load_4d_w(sK + g.nband * S::SLOT_BYTES, &tmK, bar_ld, 0, 0, h, b);
+        tma_load_4d_w(sV + g.nband * S::SLOT_BYTES, &tmV, bar_ld, 0, 0, h, b);
       }
 
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
                      g_addr = smem_u32(sG);
-      const uint32_t idesc_s = make_idesc(kTile, kBlock, Elem<T>::fmt, 0, 0);
       const uint32_t idesc_dq = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
-      auto issue_s_dp = [&](int c) {   // chunk c: S and dP of up to 3 slots, one N=32 MMA chain per slot
-        for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {
-          const int j = order(c * PASS + i);
-          if (!slot_valid(j)) continue;
+      auto issue_s_dp = [&](int c) {   // chunk c: S and dP of up to 3 contiguous slots, one N = 32*cnt MMA chain each
+        const int cnt = (ns - c * PASS) < PASS ? (ns - c * PASS) : PASS;
+        const uint32_t idesc_s = make_idesc(kTile, cnt * kBlock, Elem<T>::fmt, 0, 0);
+        const uint32_t koff = c * PASS * S::SLOT_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < DH / 16; ++ks) {
-            mma_ss(tmem_base + S::COL_S + 32 * i, make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB),
-                   make_smem_desc(k_addr + j * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
-            mma_ss(tmem_base + S::COL_DP + 32 * i, make_smem_desc(do_addr + ks * 32, 16, 8 * ROWB, ROWB),
-                   make_smem_desc(v_addr + j * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
-          }
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          mma_ss_w(tmem_base + S::COL_S, make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB),
+                   make_smem_desc(k_addr + koff + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
+          mma_ss_w(tmem_base + S::COL_DP, make_smem_desc(do_addr + ks * 32, 16, 8 * ROWB, ROWB),
+                   make_smem_desc(v_addr + koff + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
         }
       };
 
       mbar_wait(bar_ld, 0);
       tc_fence_after();
       issue_s_dp(0);
-      tc_commit(bar_sdp + 0);
+      tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_ds + c, 0);
@@ -146,14 +146,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (!slot_valid(j)) continue;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            mma_ts(tmem_base + S::COL_DQ, tmem_base + S::COL_S + 16 * i + 8 * s,
+            mma_ts_w(tmem_base + S::COL_DQ, tmem_base + S::COL_S + 16 * i + 8 * s,
                    make_smem_desc(k_addr + j * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB), idesc_dq, acc);
             acc = 1;
           }
         }
         if (c + 1 < npass) {
           issue_s_dp(c + 1);            // in-order tensor pipe: overwrites the chunk's S/dS only after the dQ MMAs read it
-          tc_commit(bar_sdp + c + 1);
+          tc_commit_w(bar_sdp + c + 1);
         } else {
           if (g.cls) {
             // G[128 x 64] = [dO^T ; Q^T][128 x 128q] * [P_0 | dS_0][128q x 64] ; both operands MN-major.
@@ -161,10 +161,10 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const uint32_t idesc_g = make_idesc(kTile, 64, Elem<T>::fmt, 1, 1);
 #pragma unroll
             for (int s = 0; s < kTile / 16; ++s)
-              mma_ss(tmem_base + S::COL_G, make_smem_desc(do_addr + s * 16 * ROWB, S::TILE_BYTES, 8 * ROWB, ROWB),
+              mma_ss_w(tmem_base + S::COL_G, make_smem_desc(do_addr + s * 16 * ROWB, S::TILE_BYTES, 8 * ROWB, ROWB),
                      make_smem_desc(g_addr + s * 16 * 128, 16 * 128, 8 * 128, 128), idesc_g, s > 0 ? 1u : 0u);
           }
-          tc_commit(bar_dq);
+          tc_commit_w(bar_dq);
         }
       }
     }
@@ -208,8 +208,8 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
     auto slot_live = [&](int j) {
       if (r >= g.nb || !slot_valid(j)) return false;
-      if (g.cls && j == 0) return true;
-      const int blk = band_lo + j - g.cls;
+      if (is_global(j)) return true;
+      const int blk = band_lo + j;
       return blk >= r - (g.left - 1) && blk <= r + g.nsup;
     };
     const uint32_t below_diag = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);   // bit c set <=> key c <= query lane
@@ -220,7 +220,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       bool wrote_g = false;
       for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {
         const int j = order(c * PASS + i);
-        const bool is_g = g.cls && j == 0;
+        const bool is_g = is_global(j);
         uint32_t dsk[16];
         if (slot_live(j)) {
           uint32_t sv[32], dv[32], pk[16];
@@ -355,7 +355,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   uint64_t* bar_pds = bars + 6;     // [4], 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const TileGeom g = p.g;
   const int nq = g.nband;
@@ -383,12 +383,12 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar_ld, 2 * S::TILE_BYTES + 2 * nq * S::SLOT_BYTES);
-      tma_load_4d(sK, &tmK, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d(sV, &tmV, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d(sQ, &tmQband, bar_ld, 0, q_lo * kBlock, h, b);      // rows outside [0, L) -> zeros
-      tma_load_4d(sDO, &tmDOband, bar_ld, 0, q_lo * kBlock, h, b);
+    {   // warp-convergent issue path
+      mbar_arrive_expect_tx_w(bar_ld, 2 * S::TILE_BYTES + 2 * nq * S::SLOT_BYTES);
+      tma_load_4d_w(sK, &tmK, bar_ld, 0, t * kTile, h, b);
+      tma_load_4d_w(sV, &tmV, bar_ld, 0, t * kTile, h, b);
+      tma_load_4d_w(sQ, &tmQband, bar_ld, 0, q_lo * kBlock, h, b);      // rows outside [0, L) -> zeros
+      tma_load_4d_w(sDO, &tmDOband, bar_ld, 0, q_lo * kBlock, h, b);
 
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       const uint32_t idesc_o = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
@@ -397,16 +397,16 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         const uint32_t idesc_s = make_idesc(kTile, cnt * kBlock, Elem<T>::fmt, 0, 0);
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
-          mma_ss(tmem_base + S::COL_ST, make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, ROWB),
+          mma_ss_w(tmem_base + S::COL_ST, make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, ROWB),
                  make_smem_desc(q_addr + c * PASS * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
-          mma_ss(tmem_base + S::COL_DPT, make_smem_desc(v_addr + ks * 32, 16, 8 * ROWB, ROWB),
+          mma_ss_w(tmem_base + S::COL_DPT, make_smem_desc(v_addr + ks * 32, 16, 8 * ROWB, ROWB),
                  make_smem_desc(do_addr + c * PASS * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
         }
       };
       mbar_wait(bar_ld, 0);
       tc_fence_after();
       issue_s_dp(0);
-      tc_commit(bar_sdp + 0);
+      tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_pds + c, 0);
@@ -416,18 +416,18 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             // dV += P^T dO ; dK += dS^T Q   (B operands: the dO / Q slots, MN-major)
-            mma_ts(tmem_base + S::COL_DV, tmem_base + S::COL_ST + 16 * i + 8 * s,
+            mma_ts_w(tmem_base + S::COL_DV, tmem_base + S::COL_ST + 16 * i + 8 * s,
                    make_smem_desc(do_addr + slot * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB), idesc_o, acc);
-            mma_ts(tmem_base + S::COL_DK, tmem_base + S::COL_DPT + 16 * i + 8 * s,
+            mma_ts_w(tmem_base + S::COL_DK, tmem_base + S::COL_DPT + 16 * i + 8 * s,
                    make_smem_desc(q_addr + slot * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB), idesc_o, acc);
             acc = 1;
           }
         }
         if (c + 1 < npass) {
           issue_s_dp(c + 1);
-          tc_commit(bar_sdp + c + 1);
+          tc_commit_w(bar_sdp + c + 1);
         } else {
-          tc_commit(bar_out);
+          tc_commit_w(bar_out);
         }
       }
     }

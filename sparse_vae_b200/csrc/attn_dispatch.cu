@@ -15,6 +15,8 @@ int exact_bwd(const svae_attn_desc*, const void*, const void*, const void*, cons
 namespace sm100 {
 
 int fwd(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, float*, long long*, cudaStream_t);
+bool fwd_persist_supported(const svae_attn_desc*);
+int fwd_persist(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, long long*, cudaStream_t);
 size_t bwd_workspace(const svae_attn_desc*);
 bool bwd_supported(const svae_attn_desc*);
 int bwd(const svae_attn_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
@@ -112,6 +114,9 @@ static int attn_fwd_impl(const svae_attn_desc* d, const void* q, const void* k, 
   SVAE_REQUIRE(tma_ok(q, d->q_stride, d->heads, d->batch, d->seq_len) && tma_ok(k, d->k_stride, d->heads, d->batch, d->seq_len) &&
                    tma_ok(v, d->v_stride, d->heads, d->batch, d->seq_len) && tma_ok(out, d->o_stride, d->heads, d->batch, d->seq_len),
                SVAE_ERR_INVALID, "svae_attn_fwd: 16-bit tensors must be 16-byte aligned with strides that are multiples of 8 elements");
+  // opt-in: persistent warp-specialised kernel (measured slower than two resident one-tile CTAs so far)
+  if (!s_dump && (d->flags & SVAE_ATTN_PERSISTENT) && sm100::fwd_persist_supported(d))
+    return sm100::fwd_persist(d, q, k, v, kpm, out, lse, timeline, st);
   return sm100::fwd(d, q, k, v, kpm, out, lse, s_dump, timeline, st);
 }
 

@@ -1,0 +1,399 @@
+// Persistent, warp-specialised variant of the fused block-sparse attention forward (sm_100a), used for the
+// reference's default geometry (<= 8 key slots per 128-query tile, <= 4 live band blocks per block-row).
+//
+// One CTA per SM walks over query tiles (tile = blockIdx.x + i * gridDim.x) with TWO tiles in flight:
+//   warp  8      TMA producer for Q + K (2-deep ring, refilled as soon as the S = Q K^T MMAs of a tile retire)
+//   warp  9      TMA producer for V     (2-deep ring, refilled when both P V chains of a tile retire)
+//   warp 10      tcgen05.mma issuer: S(i) = Q K^T, then the even-slot half of O(i-1) = P V
+//   warps 0-3    softmax group 0 (tiles 0, 2, 4, ...), warps 4-7: softmax group 1 (tiles 1, 3, ...): one batch of
+//                tcgen05.ld of the block-row's live slots, register-resident two-pass softmax, P written over S,
+//                warp 0 of the group issues the odd-slot half of P V, epilogue (O_even + O_odd) / l -> SMEM -> TMA store
+// TMEM: 2 x 256 columns (per tile: S 256 | P aliases 0-127 | O_even 128-191 | O_odd 192-255).
+// Registers are rebalanced with setmaxnreg (softmax warpgroups 232, producer/MMA warpgroup 40) so the 160 live
+// scores of a row stay in registers.  While group 0 runs the CUDA-core softmax of tile i, the tensor pipe computes
+// S(i+1) and the TMA engine is already fetching tile i+2: load latency, MMA and softmax of different tiles overlap
+// inside one SM without relying on a second resident CTA.  Same arithmetic as attn_fwd_sm100_kernel.
+#include "attn_sm100.cuh"
+
+namespace svae {
+namespace sm100 {
+
+using namespace ptx;
+
+constexpr int kPersistThreads = 384;     // 3 warpgroups: softmax 0, softmax 1, {TMA QK, TMA V, MMA, spare}
+
+template <int DH>
+struct FwdPSmem {
+  static constexpr int NS = 8;
+  static constexpr int ROWB = DH * 2;
+  static constexpr int Q_BYTES = kTile * ROWB;
+  static constexpr int SLOT_BYTES = kBlock * ROWB;
+  static constexpr int KV_BYTES = NS * SLOT_BYTES;
+  static constexpr int OFF_Q = 0;                            // [2]
+  static constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;          // [2]
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;         // [2]
+  static constexpr int OFF_OST = OFF_V + 2 * KV_BYTES;       // [2] output staging
+  static constexpr int OFF_KPM = OFF_OST + 2 * Q_BYTES;      // [2]
+  static constexpr int OFF_BAR = OFF_KPM + 2 * NS * kBlock * 4;
+  static constexpr int DYN_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int O_COL = 128, O2_COL = 192;
+  static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
+};
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKband,
+                              const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmO,
+                              const FwdParams p, const int tiles_per_seq, const int num_tiles) {
+  using S = FwdPSmem<DH>;
+  constexpr int ROWB = S::ROWB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* qk_full = bars + 0;     // [2] TMA -> MMA
+  uint64_t* v_full = bars + 2;      // [2] TMA -> MMA / chain-B warp
+  uint64_t* qk_free = bars + 4;     // [2] MMA (S retired) -> Q/K producer
+  uint64_t* v_free = bars + 6;      // [2] both P V chains retired -> V producer            (2 arrivals)
+  uint64_t* s_ready = bars + 8;     // [2] MMA -> softmax group
+  uint64_t* p_ready = bars + 10;    // [2] softmax group -> MMA / chain-B warp              (128 arrivals)
+  uint64_t* o_ready = bars + 12;    // [2] both P V chains retired -> softmax group          (2 arrivals)
+  uint64_t* tmem_free = bars + 14;  // [2] group has read O: TMEM half reusable              (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = warp_index(), lane = threadIdx.x & 31;
+  const TileGeom g = p.g;
+  const int ns = g.nslots;
+  const int nt = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(qk_full + k, 1); mbar_init(v_full + k, 1); mbar_init(qk_free + k, 1); mbar_init(v_free + k, 2);
+      mbar_init(s_ready + k, 1); mbar_init(p_ready + k, 128); mbar_init(o_ready + k, 2); mbar_init(tmem_free + k, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 11) {
+    if (lane == 0) {
+      prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
+      prefetch_tensormap(&tmKband); prefetch_tensormap(&tmVband); prefetch_tensormap(&tmO);
+    }
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int i, int& t, int& h, int& b) {
+    const int id = (int)blockIdx.x + i * (int)gridDim.x;
+    t = id % tiles_per_seq;
+    const int bh = id / tiles_per_seq;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
+  const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
+  // O (+)= P_j V_j for slots j = first, first + 2, ... of the tile in ring slot k
+  auto issue_pv_chain = [&](int k, int first, uint32_t o_col) {
+    const uint32_t v_addr = smem_u32(smem + S::OFF_V + k * S::KV_BYTES);
+    const uint32_t tb = tmem_base + 256 * k;
+    uint32_t acc = 0;
+    for (int j = first; j < ns; j += 2) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uint64_t bd = make_smem_desc(v_addr + j * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB);
+        mma_ts_w(tb + o_col, tb + 16 * j + 8 * s, bd, idesc_pv, acc);
+        acc = 1;
+      }
+    }
+  };
+
+  if (warp >= 8) {
+    // ======================================= producer / MMA warpgroup =======================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 8) {
+      for (int i = 0; i < nt; ++i) {
+        const int k = i & 1, n = i >> 1;
+        int t, h, b;
+        tile_coords(i, t, h, b);
+        const int band_lo = 4 * t - (g.left - 1);
+        long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 1) * 8 : nullptr;
+        if (tl) tl[0] = clock64();
+        if (i >= 2) mbar_wait(qk_free + k, (n - 1) & 1);
+        if (tl) tl[1] = clock64();
+        uint8_t* sQ = smem + S::OFF_Q + k * S::Q_BYTES;
+        uint8_t* sK = smem + S::OFF_K + k * S::KV_BYTES;
+        mbar_arrive_expect_tx_w(qk_full + k, S::Q_BYTES + ns * S::SLOT_BYTES);
+        tma_load_4d_w(sQ, &tmQ, qk_full + k, 0, t * kTile, h, b);
+        tma_load_4d_w(sK + g.cls * S::SLOT_BYTES, &tmKband, qk_full + k, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
+        if (g.cls) tma_load_4d_w(sK, &tmK, qk_full + k, 0, 0, h, b);
+        if (tl) tl[2] = clock64();
+      }
+    } else if (warp == 9) {
+      for (int i = 0; i < nt; ++i) {
+        const int k = i & 1, n = i >> 1;
+        int t, h, b;
+        tile_coords(i, t, h, b);
+        const int band_lo = 4 * t - (g.left - 1);
+        long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 2) * 8 : nullptr;
+        if (tl) tl[0] = clock64();
+        if (i >= 2) mbar_wait(v_free + k, (n - 1) & 1);
+        if (tl) tl[1] = clock64();
+        uint8_t* sV = smem + S::OFF_V + k * S::KV_BYTES;
+        mbar_arrive_expect_tx_w(v_full + k, ns * S::SLOT_BYTES);
+        tma_load_4d_w(sV + g.cls * S::SLOT_BYTES, &tmVband, v_full + k, 0, band_lo * kBlock, h, b);
+        if (g.cls) tma_load_4d_w(sV, &tmV, v_full + k, 0, 0, h, b);
+        if (tl) tl[2] = clock64();
+      }
+    } else if (warp == 10) {
+      const uint32_t idesc_s = make_idesc(kTile, ns * kBlock, Elem<T>::fmt, 0, 0);
+      for (int i = 0; i <= nt; ++i) {
+        if (i < nt) {
+          // ---- S(i) = Q K^T into TMEM half k
+          const int k = i & 1, n = i >> 1;
+          long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 4) * 8 : nullptr;
+          if (tl) tl[0] = clock64();
+          mbar_wait(qk_full + k, n & 1);
+          if (tl) tl[1] = clock64();
+          if (i >= 2) mbar_wait(tmem_free + k, (n - 1) & 1);
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(smem + S::OFF_Q + k * S::Q_BYTES);
+          const uint32_t k_addr = smem_u32(smem + S::OFF_K + k * S::KV_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks)
+            mma_ss_w(tmem_base + 256 * k, make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB),
+                     make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
+          tc_commit_w(s_ready + k);
+          tc_commit_w(qk_free + k);
+          if (tl) tl[2] = clock64();
+        }
+        if (i >= 1) {
+          // ---- even-slot half of O(i-1) = P V
+          const int k = (i - 1) & 1, n = (i - 1) >> 1;
+          long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)(i - 1) * gridDim.x) * 5 + 4) * 8 : nullptr;
+          if (tl) tl[3] = clock64();
+          mbar_wait(p_ready + k, n & 1);
+          mbar_wait(v_full + k, n & 1);
+          tc_fence_after();
+          if (tl) tl[4] = clock64();
+          issue_pv_chain(k, 0, S::O_COL);
+          tc_commit_w(o_ready + k);
+          tc_commit_w(v_free + k);
+          if (tl) tl[5] = clock64();
+        }
+      }
+    }
+  } else {
+    // ======================================= softmax warpgroups =============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int grp = warp >> 2;                 // 0 or 1 = ring slot / TMEM half of this group's tiles
+    const int w = warp & 3;                    // TMEM lane quarter = block-row inside the tile
+    const int tid_g = threadIdx.x & 127;
+    const int row = w * 32 + lane;
+    const uint32_t tb = tmem_base + 256 * grp;
+    const uint32_t trow = tb + ((uint32_t)(w * 32) << 16);
+    float* sKpm = reinterpret_cast<float*>(smem + S::OFF_KPM) + grp * (S::NS * kBlock);
+    uint8_t* sOst = smem + S::OFF_OST + grp * S::Q_BYTES;
+    const uint32_t below_diag = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);   // bit c set <=> key c <= query lane
+    const int nlb = g.left + g.nsup;           // live band slots per block-row (<= 4)
+    const int first = g.cls + w;
+    const int kdiag = g.causal ? g.left - 1 : -1;
+
+    for (int i = grp; i < nt; i += 2) {
+      const int n = i >> 1;
+      int t, h, b;
+      tile_coords(i, t, h, b);
+      const int r0 = 4 * t, r = r0 + w;
+      const int band_lo = r0 - (g.left - 1);
+      const int qpos = t * kTile + row;
+      auto slot_valid = [&](int j) {
+        if (g.cls && j == 0) return true;
+        int blk = band_lo + j - g.cls;
+        return blk >= g.cls && blk < g.nb;
+      };
+
+      // stage the additive key-padding mask of the tile's keys (log2 domain); all-zero -> fast path
+      uint32_t any_kpm = 0;
+      if (p.kpm) {
+        for (int e = tid_g; e < ns * kBlock; e += 128) {
+          const int j = e >> 5, c = e & 31;
+          float kv = 0.f;
+          if (slot_valid(j)) {
+            const int blk = (g.cls && j == 0) ? 0 : band_lo + j - g.cls;
+            kv = p.kpm[(int64_t)b * p.L + blk * kBlock + c] * kLog2e;
+          }
+          sKpm[e] = kv;
+          any_kpm |= (kv != 0.f) ? 1u : 0u;
+        }
+      }
+      const bool has_kpm = bar_red_or(1 + grp, 128, any_kpm);
+
+      const bool lg = g.cls && r < g.nb;
+      bool lv[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) lv[kk] = kk < nlb && r < g.nb && slot_valid(first + kk);
+
+      long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + w) * 8 : nullptr;
+      if (tl) tl[0] = clock64();
+      mbar_wait(s_ready + grp, n & 1);
+      tc_fence_after();
+      if (tl) tl[1] = clock64();
+      uint32_t sg[32], s0[32], s1[32], s2[32], s3[32];
+      if (lg) tmem_ld32(trow, sg);
+      if (lv[0]) tmem_ld32(trow + 32 * (first + 0), s0);
+      if (lv[1]) tmem_ld32(trow + 32 * (first + 1), s1);
+      if (lv[2]) tmem_ld32(trow + 32 * (first + 2), s2);
+      if (lv[3]) tmem_ld32(trow + 32 * (first + 3), s3);
+      tmem_wait_ld();
+      tmem_dep(sg); tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
+      if (kdiag == 0 && lv[0]) mask_above_diag(s0, below_diag);
+      if (kdiag == 1 && lv[1]) mask_above_diag(s1, below_diag);
+      if (kdiag == 2 && lv[2]) mask_above_diag(s2, below_diag);
+      if (kdiag == 3 && lv[3]) mask_above_diag(s3, below_diag);
+      if (g.causal && g.cls && r == 0 && lg) mask_above_diag(sg, below_diag);   // block-row 0: the global block IS the diagonal
+
+      float m = -INFINITY, l0 = 0.f, l1 = 0.f;
+      if (lg) m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
+      if (lv[0]) m = slot_max(s0, m, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2);
+      if (lv[1]) m = slot_max(s1, m, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2);
+      if (lv[2]) m = slot_max(s2, m, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2);
+      if (lv[3]) m = slot_max(s3, m, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2);
+      if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
+      const float neg_m = (m == -INFINITY) ? 0.f : -m;
+      if (tl) tl[2] = clock64();
+
+      uint32_t pk[16];
+      if (lg) { slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m); tmem_st16(trow, pk); }
+      if (lv[0]) { slot_exp_pack<T>(s0, pk, l0, l1, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 0), pk); }
+      if (lv[1]) { slot_exp_pack<T>(s1, pk, l0, l1, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 1), pk); }
+      if (lv[2]) { slot_exp_pack<T>(s2, pk, l0, l1, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 2), pk); }
+      if (lv[3]) { slot_exp_pack<T>(s3, pk, l0, l1, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 3), pk); }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pk[c] = 0u;
+      uint32_t live_mask = lg ? 1u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) live_mask |= lv[kk] ? (1u << (first + kk)) : 0u;
+      for (int j = 0; j < ns; ++j)              // P = 0 for the slots this block-row does not attend
+        if (!((live_mask >> j) & 1u)) tmem_st16(trow + 16 * j, pk);
+      const float l = l0 + l1;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_ready + grp);
+      if (tl) tl[3] = clock64();
+
+      if (w == 0) {
+        // ---- odd-slot half of O = P V, issued here while this warp would otherwise idle until O is ready
+        mbar_wait(p_ready + grp, n & 1);
+        mbar_wait(v_full + grp, n & 1);
+        tc_fence_after();
+        issue_pv_chain(grp, 1, S::O2_COL);
+        tc_commit_w(o_ready + grp);
+        tc_commit_w(v_free + grp);
+      }
+
+      // ---- epilogue: (O_even + O_odd) / l -> 16-bit -> swizzled staging -> TMA store ; LSE
+      if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
+      const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
+      if (tl) tl[4] = clock64();
+      mbar_wait(o_ready + grp, n & 1);
+      tc_fence_after();
+      if (tl) tl[5] = clock64();
+      uint32_t oa[32], ob[32], oc[32], od[32];
+      tmem_ld32(trow + S::O_COL, oa);
+      tmem_ld32(trow + S::O2_COL, ob);
+      if (DH == 64) {
+        tmem_ld32(trow + S::O_COL + 32, oc);
+        tmem_ld32(trow + S::O2_COL + 32, od);
+      }
+      tmem_wait_ld();
+      tmem_dep(oa); tmem_dep(ob); tmem_dep(oc); tmem_dep(od);
+      tc_fence_before();
+      mbar_arrive(tmem_free + grp);             // S / P / O of this TMEM half are consumed
+#pragma unroll
+      for (int half = 0; half < DH / 32; ++half) {
+        uint32_t (&va)[32] = half ? oc : oa;
+        uint32_t (&vb)[32] = half ? od : ob;
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (__uint_as_float(va[cq * 8 + e]) + __uint_as_float(vb[cq * 8 + e])) * inv;
+          uint4 wv;
+          wv.x = Elem<T>::pack(f[0], f[1]);
+          wv.y = Elem<T>::pack(f[2], f[3]);
+          wv.z = Elem<T>::pack(f[4], f[5]);
+          wv.w = Elem<T>::pack(f[6], f[7]);
+          *reinterpret_cast<uint4*>(sOst + swz_off<ROWB>(row, half * 4 + cq)) = wv;
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (tid_g == 32) {                        // a lane of warp 1: warp 0 is busy issuing MMAs
+        tma_store_4d(&tmO, sOst, 0, t * kTile, h, b);
+        tma_store_commit();
+        tma_store_wait_read();                  // staging tile reusable
+      }
+      named_bar_sync(1 + grp, 128);             // nobody overwrites the staging tile before the store has read it
+      if (tl) tl[6] = clock64();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) tmem_dealloc<512>(tmem_base);
+}
+
+template <typename T, int DH>
+static int launch_fwd_persist(const svae_attn_desc* d, const TileGeom& g, const void* q, const void* k, const void* v,
+                              const float* kpm, void* out, float* lse, long long* timeline, cudaStream_t st) {
+  using S = FwdPSmem<DH>;
+  CUtensorMap tmQ, tmK, tmV, tmKb, tmVb, tmO;
+  int rc;
+  const int band_rows = g.nband * kBlock;
+  if ((rc = encode_tmap(&tmQ, Elem<T>::tm, q, DH, d->seq_len, d->heads, d->batch, d->q_stride, kTile))) return rc;
+  if ((rc = encode_tmap(&tmK, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, kBlock))) return rc;
+  if ((rc = encode_tmap(&tmV, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, kBlock))) return rc;
+  if ((rc = encode_tmap(&tmKb, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, band_rows))) return rc;
+  if ((rc = encode_tmap(&tmVb, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, band_rows))) return rc;
+  if ((rc = encode_tmap(&tmO, Elem<T>::tm, out, DH, d->seq_len, d->heads, d->batch, d->o_stride, kTile))) return rc;
+  FwdParams p;
+  p.kpm = kpm; p.lse = lse; p.s_dump = nullptr; p.timeline = timeline;
+  p.L = d->seq_len; p.H = d->heads; p.g = g;
+  p.scale_log2 = d->scale * kLog2e;
+  auto kern = attn_fwd_persist_sm100_kernel<T, DH>;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0, n = 0;
+    SVAE_CUDA_CHECK(cudaGetDevice(&dev));
+    SVAE_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+    sm_count = n;
+  }
+  const int tiles_per_seq = (d->seq_len + kTile - 1) / kTile;
+  const int num_tiles = tiles_per_seq * d->heads * d->batch;
+  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  ScopedKernelTimer timer("attn_fwd_sm100", st);
+  kern<<<grid, kPersistThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmKb, tmVb, tmO, p, tiles_per_seq, num_tiles);
+  SVAE_CUDA_CHECK(cudaGetLastError());
+  return SVAE_OK;
+}
+
+bool fwd_persist_supported(const svae_attn_desc* d) {
+  if (d->dtype != SVAE_DTYPE_BF16 && d->dtype != SVAE_DTYPE_F16) return false;
+  if (d->head_dim != 64 && d->head_dim != 32) return false;
+  const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
+  return g.nslots <= 8 && g.left + g.nsup <= 4 && d->scale > 0.f;
+}
+
+int fwd_persist(const svae_attn_desc* d, const void* q, const void* k, const void* v, const float* kpm, void* out,
+                float* lse, long long* timeline, cudaStream_t st) {
+  const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
+  if (d->dtype == SVAE_DTYPE_BF16)
+    return d->head_dim == 64 ? launch_fwd_persist<__nv_bfloat16, 64>(d, g, q, k, v, kpm, out, lse, timeline, st)
+                             : launch_fwd_persist<__nv_bfloat16, 32>(d, g, q, k, v, kpm, out, lse, timeline, st);
+  return d->head_dim == 64 ? launch_fwd_persist<__half, 64>(d, g, q, k, v, kpm, out, lse, timeline, st)
+                           : launch_fwd_persist<__half, 32>(d, g, q, k, v, kpm, out, lse, timeline, st);
+}
+
+}  // namespace sm100
+}  // namespace svae

@@ -5,12 +5,14 @@
 //
 // One CTA = one 128-query tile (4 block-rows of the 32x32 layout) of one (batch, head).  The union of key blocks
 // those 4 block-rows attend is a contiguous band of (left+3+nsup) blocks plus the global block 0, i.e. <= 8 "slots"
-// of 32 keys at window 4; all of it fits TMEM at once (128 lanes x 32*slots fp32 columns), so the softmax is a
-// plain two-pass row softmax over the LIVE slots of the warp's block-row -- each of the 4 softmax warps owns
-// exactly one block-row (TMEM lane quarter), so block-level sparsity is warp-uniform and dead blocks cost nothing
-// on the CUDA cores.  TMEM budget: S [0, 32*slots) ; P aliases S in place (in-order overwrite) ; O in a dead
-// part of S.  <= 256 columns -> two CTAs per SM overlap each other's load / MMA / softmax / store phases.
-// The whole band arrives with ONE TMA box per operand (rows outside [0, L) are zero-filled by the TMA unit).
+// of 32 keys at window 4; all of it fits TMEM at once (128 lanes x 32*slots fp32 columns).  Each of the 4 softmax
+// warps owns exactly one block-row (TMEM lane quarter), so block sparsity is warp-uniform: a warp pulls only its
+// LIVE slots (<= 4 band + global) out of TMEM in ONE batch of tcgen05.ld, keeps them in registers for the max and
+// the exp pass, and dead blocks cost nothing on the CUDA cores.
+// TMEM budget: S [0, 32*slots) ; P aliases S ; two O accumulators in dead S columns (the P V chain is split over two
+// issuing warps because one thread retires a TMEM-operand MMA only every ~123 cycles).  <= 256 columns -> two CTAs
+// per SM overlap each other's load / MMA / softmax / store phases.  The whole band arrives with ONE TMA box per
+// operand (rows outside [0, L) are zero-filled by the TMA unit).  All TMA / MMA issue is warp-convergent.
 //
 // Roofline: HBM-bound (AI ~ 79 FLOP/B at window 4, ridge ~ 215): algorithmic bytes = 4 * B*L*H*Dh * 2 per launch.
 #include "attn_sm100.cuh"
@@ -32,35 +34,24 @@ struct FwdSmem {
   static constexpr int OFF_BAR = OFF_KPM + NSMAX * kBlock * 4;
   static constexpr int TOTAL = OFF_BAR + 64;
   static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024-byte alignment
+  static constexpr bool kTwoChains = NSMAX <= 8;
   static constexpr int TMEM_COLS = NSMAX <= 8 ? 256 : 512;
   static constexpr int O_COL = NSMAX <= 8 ? 128 : 448;
-  static_assert(NSMAX * kBlock <= O_COL || NSMAX <= 8, "S must not overlap O when they are both live");
+  static constexpr int O2_COL = 192;               // second accumulator (two-chain variant only)
   static_assert(O_COL + DH <= TMEM_COLS, "O does not fit");
   static_assert(NSMAX * kBlock / 2 <= O_COL, "P must not overlap O");
 };
-
-// max over one 32-column slot of raw scores (4 independent chains, 3-input max)
-__device__ __forceinline__ float slot_max_raw(const uint32_t (&v)[32], float m) {
-  float a = m, b = -INFINITY, c = -INFINITY, d = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    a = fmax3(a, __uint_as_float(v[i + 0]), __uint_as_float(v[i + 1]));
-    b = fmax3(b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-    c = fmax3(c, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-    d = fmax3(d, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-  }
-  return fmax3(fmaxf(a, b), c, d);
-}
 
 template <typename T, int DH, int NSMAX>
 __global__ void __launch_bounds__(kThreads, NSMAX <= 8 ? 2 : 1)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKband,
-                      const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmO,
+                      const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmKband2,
+                      const __grid_constant__ CUtensorMap tmVband2, const __grid_constant__ CUtensorMap tmO,
                       const FwdParams p) {
   using S = FwdSmem<DH, NSMAX>;
   constexpr int ROWB = S::ROWB;
-  constexpr bool kBandTma = NSMAX <= 8;     // the band (<= 8 slots = 256 rows) fits one TMA box
+  constexpr bool kTwoChains = S::kTwoChains;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + S::OFF_Q;
@@ -72,10 +63,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* bar_v = bars + 1;    // TMA: V slots landed
   uint64_t* bar_s = bars + 2;    // MMA: S complete in TMEM
   uint64_t* bar_p = bars + 3;    // softmax: P written to TMEM (128 arrivals)
-  uint64_t* bar_o = bars + 4;    // MMA: O complete in TMEM
+  uint64_t* bar_o = bars + 4;    // MMA: O complete in TMEM (one arrival per P V chain)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_index(), lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const TileGeom g = p.g;
   const int ns = g.nslots;
@@ -88,7 +79,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   stamp(0);
 
   auto slot_block = [&](int j) { return (g.cls && j == 0) ? 0 : band_lo + j - g.cls; };
-  // a slot carries keys the tile may attend: inside the sequence and not a duplicate of the global block
+  // a slot carries keys the tile may attend: inside the sequence and not a duplicate of the global block.
+  // (every slot is LOADED -- out-of-range rows arrive as zeros -- so invalid slots only need P = 0)
   auto slot_valid = [&](int j) {
     if (g.cls && j == 0) return true;
     int blk = band_lo + j - g.cls;
@@ -100,7 +92,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
-    mbar_init(bar_o, 1);
+    mbar_init(bar_o, kTwoChains ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 4) {
@@ -120,71 +112,71 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   stamp(1);
 
-  if (warp == 4) {
-    // ================= producer + MMA issuer (one elected lane) =================
-    if (lane == 0) {
-      if (kBandTma) {
-        // one box for the whole band; rows < 0 or >= L come back as zeros, so every slot holds finite data
-        mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + ns * S::SLOT_BYTES);
-        tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
-        tma_load_4d(sK + g.cls * S::SLOT_BYTES, &tmKband, bar_qk, 0, band_lo * kBlock, h, b);
-        if (g.cls) tma_load_4d(sK, &tmK, bar_qk, 0, 0, h, b);
-        mbar_arrive_expect_tx(bar_v, ns * S::SLOT_BYTES);
-        tma_load_4d(sV + g.cls * S::SLOT_BYTES, &tmVband, bar_v, 0, band_lo * kBlock, h, b);
-        if (g.cls) tma_load_4d(sV, &tmV, bar_v, 0, 0, h, b);
-      } else {
-        int nvalid = 0;
-        for (int j = 0; j < ns; ++j) nvalid += slot_valid(j) ? 1 : 0;
-        mbar_arrive_expect_tx(bar_qk, S::Q_BYTES + nvalid * S::SLOT_BYTES);
-        tma_load_4d(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
-        for (int j = 0; j < ns; ++j)
-          if (slot_valid(j)) tma_load_4d(sK + j * S::SLOT_BYTES, &tmK, bar_qk, 0, slot_block(j) * kBlock, h, b);
-        mbar_arrive_expect_tx(bar_v, nvalid * S::SLOT_BYTES);
-        for (int j = 0; j < ns; ++j)
-          if (slot_valid(j)) tma_load_4d(sV + j * S::SLOT_BYTES, &tmV, bar_v, 0, slot_block(j) * kBlock, h, b);
-      }
-
-      stamp(2);
-      // ---- S = Q K^T : M = 128, N = 32*ns (split at 256), K = DH in steps of 16
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      stamp(3);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const int ntot = ns * kBlock;
-      for (int n0 = 0; n0 < ntot; n0 += 256) {
-        const int n = (ntot - n0) < 256 ? (ntot - n0) : 256;
-        const uint32_t idesc = make_idesc(kTile, n, Elem<T>::fmt, 0, 0);
+  const uint32_t v_addr = smem_u32(sV);
+  const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
+  // O (+)= P_j V_j for slots j = first, first + step, ... : A = P from TMEM (8 columns per 16 keys), B = V slot MN-major
+  auto issue_pv_chain = [&](int first, int step, uint32_t o_col) {
+    uint32_t acc = 0;
+    for (int j = first; j < ns; j += step) {
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint64_t ad = make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB);
-          const uint64_t bd = make_smem_desc(k_addr + n0 * ROWB + ks * 32, 16, 8 * ROWB, ROWB);
-          mma_ss(tmem_base + n0, ad, bd, idesc, ks > 0 ? 1u : 0u);
-        }
+      for (int s = 0; s < 2; ++s) {
+        const uint64_t bd = make_smem_desc(v_addr + j * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB);
+        mma_ts_w(tmem_base + o_col, tmem_base + 16 * j + 8 * s, bd, idesc_pv, acc);
+        acc = 1;
       }
-      tc_commit(bar_s);
-      stamp(4);
-
-      // ---- O = P V : A = P from TMEM (16-bit, 8 columns per 16 keys), B = V slot (MN-major), N = DH
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
-      stamp(5);
-      const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
-      uint32_t acc = 0;
-      for (int j = 0; j < ns; ++j) {
-        if (!slot_valid(j)) continue;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const uint64_t bd = make_smem_desc(v_addr + j * S::SLOT_BYTES + s * 16 * ROWB, S::SLOT_BYTES, 8 * ROWB, ROWB);
-          mma_ts(tmem_base + S::O_COL, tmem_base + 16 * j + 8 * s, bd, idesc_pv, acc);
-          acc = 1;
-        }
-      }
-      tc_commit(bar_o);
-      stamp(6);
-      if (tl) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tl[7] = (long long)((gt << 8) | (smid & 255)); }
     }
-    __syncwarp();
+  };
+
+  if (warp == 4) {
+    // ================= producer + MMA issuer: the whole warp runs this convergently, one lane is elected per op ====
+    const int band_slots = ns - g.cls;
+    const int box1 = band_slots < 8 ? band_slots : 8;
+    mbar_arrive_expect_tx_w(bar_qk, S::Q_BYTES + ns * S::SLOT_BYTES);
+    tma_load_4d_w(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
+    tma_load_4d_w(sK + g.cls * S::SLOT_BYTES, &tmKband, bar_qk, 0, band_lo * kBlock, h, b);    // OOB rows -> zeros
+    if (band_slots > 8) tma_load_4d_w(sK + (g.cls + 8) * S::SLOT_BYTES, &tmKband2, bar_qk, 0, (band_lo + 8) * kBlock, h, b);
+    if (g.cls) tma_load_4d_w(sK, &tmK, bar_qk, 0, 0, h, b);
+    mbar_arrive_expect_tx_w(bar_v, ns * S::SLOT_BYTES);
+    tma_load_4d_w(sV + g.cls * S::SLOT_BYTES, &tmVband, bar_v, 0, band_lo * kBlock, h, b);
+    if (band_slots > 8) tma_load_4d_w(sV + (g.cls + 8) * S::SLOT_BYTES, &tmVband2, bar_v, 0, (band_lo + 8) * kBlock, h, b);
+    if (g.cls) tma_load_4d_w(sV, &tmV, bar_v, 0, 0, h, b);
+    (void)box1;
+    stamp(2);
+
+    // ---- S = Q K^T : M = 128, N = 32*ns (split at 256), K = DH in steps of 16
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    stamp(3);
+    const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK);
+    const int ntot = ns * kBlock;
+    for (int n0 = 0; n0 < ntot; n0 += 256) {
+      const int n = (ntot - n0) < 256 ? (ntot - n0) : 256;
+      const uint32_t idesc = make_idesc(kTile, n, Elem<T>::fmt, 0, 0);
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks) {
+        const uint64_t ad = make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB);
+        const uint64_t bd = make_smem_desc(k_addr + n0 * ROWB + ks * 32, 16, 8 * ROWB, ROWB);
+        mma_ss_w(tmem_base + n0, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+    }
+    tc_commit_w(bar_s);
+    stamp(4);
+
+    // ---- O = P V, chain A (every second slot when a softmax warp issues the other half)
+    mbar_wait(bar_p, 0);
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    stamp(5);
+    issue_pv_chain(0, kTwoChains ? 2 : 1, S::O_COL);
+    tc_commit_w(bar_o);
+    stamp(6);
+    if (tl) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      tl[7] = (long long)((gt << 8) | (smid & 255));
+    }
   } else {
     // ================= softmax + epilogue warps: warp w <-> block-row r0 + w <-> TMEM lanes 32w.. =================
     const int r = r0 + warp;
@@ -230,75 +222,80 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
 
-    // ---- pass 1: row max over the live slots
-    float m = -INFINITY;                    // fast path: max of raw scores ; slow path: log2-domain max
-    for (int j = 0; j < ns; ++j) {
-      if (!slot_live(j)) continue;
-      uint32_t v[32];
-      tmem_ld32(trow + 32 * j, v);
-      tmem_wait_ld(v);
-      const bool diag = g.causal && (slot_block(j) == r);
-      if (diag) {
+    float m = -INFINITY, l0 = 0.f, l1 = 0.f, neg_m;
+    if (kTwoChains) {
+      // ---- this block-row's live slots: the global slot and band slots first .. first + nlb - 1 (nlb <= 4);
+      //      one batch of TMEM loads, scores stay in registers for both passes
+      const int nlb = g.left + g.nsup;
+      const int first = g.cls + warp;
+      const int kdiag = g.causal ? g.left - 1 : -1;              // position of the diagonal block inside the live band
+      const bool lg = g.cls && r < g.nb;
+      bool lv[4];
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (!((below_diag >> c) & 1u)) v[c] = 0xff800000u;      // -inf
-      }
-      if (!has_kpm) {
-        m = slot_max_raw(v, m);
-      } else {
-        const float* kp = sKpm + j * kBlock;
-        float a0 = m, a1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          a0 = fmaxf(a0, fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]));
-          a1 = fmaxf(a1, fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]));
-        }
-        m = fmaxf(a0, a1);
-      }
-    }
-    if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
-    stamp(3);
-    const float neg_m = (m == -INFINITY) ? 0.f : -m;
+      for (int k = 0; k < 4; ++k) lv[k] = k < nlb && r < g.nb && slot_valid(first + k);
+      uint32_t sg[32], s0[32], s1[32], s2[32], s3[32];
+      if (lg) tmem_ld32(trow, sg);
+      if (lv[0]) tmem_ld32(trow + 32 * (first + 0), s0);
+      if (lv[1]) tmem_ld32(trow + 32 * (first + 1), s1);
+      if (lv[2]) tmem_ld32(trow + 32 * (first + 2), s2);
+      if (lv[3]) tmem_ld32(trow + 32 * (first + 3), s3);
+      tmem_wait_ld();
+      tmem_dep(sg); tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
+      if (kdiag == 0 && lv[0]) mask_above_diag(s0, below_diag);
+      if (kdiag == 1 && lv[1]) mask_above_diag(s1, below_diag);
+      if (kdiag == 2 && lv[2]) mask_above_diag(s2, below_diag);
+      if (kdiag == 3 && lv[3]) mask_above_diag(s3, below_diag);
+      if (g.causal && g.cls && r == 0 && lg) mask_above_diag(sg, below_diag);   // block-row 0: the global block IS the diagonal
 
-    // ---- pass 2: P = exp2(x - m) as 16-bit pairs written over S (columns [16j, 16j+16) for slot j), row sum
-    float l0 = 0.f, l1 = 0.f;
-    for (int j = 0; j < ns; ++j) {
+      if (lg) m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
+      if (lv[0]) m = slot_max(s0, m, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2);
+      if (lv[1]) m = slot_max(s1, m, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2);
+      if (lv[2]) m = slot_max(s2, m, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2);
+      if (lv[3]) m = slot_max(s3, m, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2);
+      if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
+      neg_m = (m == -INFINITY) ? 0.f : -m;
+      stamp(3);
+
       uint32_t pk[16];
-      if (slot_live(j)) {
+      if (lg) { slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m); tmem_st16(trow, pk); }
+      if (lv[0]) { slot_exp_pack<T>(s0, pk, l0, l1, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 0), pk); }
+      if (lv[1]) { slot_exp_pack<T>(s1, pk, l0, l1, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 1), pk); }
+      if (lv[2]) { slot_exp_pack<T>(s2, pk, l0, l1, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 2), pk); }
+      if (lv[3]) { slot_exp_pack<T>(s3, pk, l0, l1, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 3), pk); }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pk[c] = 0u;
+      uint32_t live_mask = lg ? 1u : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) live_mask |= lv[k] ? (1u << (first + k)) : 0u;
+      for (int j = 0; j < ns; ++j)              // P = 0 for the slots this block-row does not attend
+        if (!((live_mask >> j) & 1u)) tmem_st16(trow + 16 * j, pk);
+    } else {
+      // ---- wide windows (9..14 slots): two passes over the live slots, one TMEM round trip per slot
+      for (int j = 0; j < ns; ++j) {
+        if (!slot_live(j)) continue;
         uint32_t v[32];
         tmem_ld32(trow + 32 * j, v);
         tmem_wait_ld(v);
-        const bool diag = g.causal && (slot_block(j) == r);
-        if (diag) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (!((below_diag >> c) & 1u)) v[c] = 0xff800000u;
-        }
-        if (!has_kpm) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), p.scale_log2, neg_m));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), p.scale_log2, neg_m));
-            l0 += p0;
-            l1 += p1;
-            pk[c >> 1] = Elem<T>::pack(p0, p1);
-          }
-        } else {
-          const float* kp = sKpm + j * kBlock;
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), p.scale_log2, kp[c]) + neg_m);
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), p.scale_log2, kp[c + 1]) + neg_m);
-            l0 += p0;
-            l1 += p1;
-            pk[c >> 1] = Elem<T>::pack(p0, p1);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pk[c] = 0u;
+        if (g.causal && slot_block(j) == r) mask_above_diag(v, below_diag);
+        m = slot_max(v, m, has_kpm, sKpm + j * kBlock, p.scale_log2);
       }
-      tmem_st16(trow + 16 * j, pk);
+      if (!has_kpm) m *= p.scale_log2;
+      neg_m = (m == -INFINITY) ? 0.f : -m;
+      stamp(3);
+      for (int j = 0; j < ns; ++j) {
+        uint32_t pk[16];
+        if (slot_live(j)) {
+          uint32_t v[32];
+          tmem_ld32(trow + 32 * j, v);
+          tmem_wait_ld(v);
+          if (g.causal && slot_block(j) == r) mask_above_diag(v, below_diag);
+          slot_exp_pack<T>(v, pk, l0, l1, has_kpm, sKpm + j * kBlock, p.scale_log2, neg_m);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) pk[c] = 0u;
+        }
+        tmem_st16(trow + 16 * j, pk);     // in-order: only overwrites S columns that were already consumed
+      }
     }
     const float l = l0 + l1;
     tmem_wait_st();
@@ -306,7 +303,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_arrive(bar_p);
     stamp(4);
 
-    // ---- epilogue: O / l -> 16-bit -> swizzled staging tile (reuses the Q buffer) -> TMA store ; LSE
+    if (kTwoChains && warp == 0) {
+      // ---- O2 = P V, chain B (odd slots), issued by this warp while it would otherwise idle until O is ready
+      mbar_wait(bar_p, 0);
+      mbar_wait(bar_v, 0);
+      tc_fence_after();
+      issue_pv_chain(1, 2, S::O2_COL);
+      tc_commit_w(bar_o);
+    }
+
+    // ---- epilogue: (O + O2) / l -> 16-bit -> swizzled staging tile (reuses the Q buffer) -> TMA store ; LSE
     if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
     const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
     mbar_wait(bar_o, 0);
@@ -316,7 +322,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int half = 0; half < DH / 32; ++half) {
       uint32_t v[32];
       tmem_ld32(trow + S::O_COL + 32 * half, v);
-      tmem_wait_ld(v);
+      if (kTwoChains) {
+        uint32_t v2[32];
+        tmem_ld32(trow + S::O2_COL + 32 * half, v2);
+        tmem_wait_ld(v, v2);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
+      } else {
+        tmem_wait_ld(v);
+      }
 #pragma unroll
       for (int cq = 0; cq < 4; ++cq) {
         uint4 w;
@@ -346,14 +360,17 @@ template <typename T, int DH, int NSMAX>
 static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q, const void* k, const void* v,
                       const float* kpm, void* out, float* lse, float* s_dump, long long* timeline, cudaStream_t st) {
   using S = FwdSmem<DH, NSMAX>;
-  CUtensorMap tmQ, tmK, tmV, tmKb, tmVb, tmO;
+  CUtensorMap tmQ, tmK, tmV, tmKb, tmVb, tmKb2, tmVb2, tmO;
   int rc;
   const int band_rows = (g.nband <= 8 ? g.nband : 8) * kBlock;
+  const int band2_rows = (g.nband > 8 ? g.nband - 8 : 1) * kBlock;
   if ((rc = encode_tmap(&tmQ, Elem<T>::tm, q, DH, d->seq_len, d->heads, d->batch, d->q_stride, kTile))) return rc;
   if ((rc = encode_tmap(&tmK, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, kBlock))) return rc;
   if ((rc = encode_tmap(&tmV, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, kBlock))) return rc;
   if ((rc = encode_tmap(&tmKb, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, band_rows))) return rc;
   if ((rc = encode_tmap(&tmVb, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, band_rows))) return rc;
+  if ((rc = encode_tmap(&tmKb2, Elem<T>::tm, k, DH, d->seq_len, d->heads, d->batch, d->k_stride, band2_rows))) return rc;
+  if ((rc = encode_tmap(&tmVb2, Elem<T>::tm, v, DH, d->seq_len, d->heads, d->batch, d->v_stride, band2_rows))) return rc;
   if ((rc = encode_tmap(&tmO, Elem<T>::tm, out, DH, d->seq_len, d->heads, d->batch, d->o_stride, kTile))) return rc;
   FwdParams p;
   p.kpm = kpm; p.lse = lse; p.s_dump = s_dump; p.timeline = timeline;
@@ -367,7 +384,7 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
   }
   dim3 grid((d->seq_len + kTile - 1) / kTile, d->heads, d->batch);
   ScopedKernelTimer timer("attn_fwd_sm100", st);
-  kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmKb, tmVb, tmO, p);
+  kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmKb, tmVb, tmKb2, tmVb2, tmO, p);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
@@ -380,9 +397,9 @@ int fwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, co
   SVAE_REQUIRE(g.nslots <= 14, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: %d key slots (window %d) exceed 14",
                g.nslots, d->window_size);
   SVAE_REQUIRE(d->scale > 0.f, SVAE_ERR_UNSUPPORTED, "sm100 attention forward: softmax scale must be positive");
-  const bool small = g.nslots <= 8;
+  const bool small = g.nslots <= 8 && g.left + g.nsup <= 4;   // the register-resident softmax holds <= 4 band slots
 #define SVAE_FWD(T, DH)                                                                              \
-  return small ? launch_fwd<T, DH, 8>(d, g, q, k, v, kpm, out, lse, s_dump, timeline, st)                      \
+  return small ? launch_fwd<T, DH, 8>(d, g, q, k, v, kpm, out, lse, s_dump, timeline, st)            \
                : launch_fwd<T, DH, 14>(d, g, q, k, v, kpm, out, lse, s_dump, timeline, st)
   if (d->dtype == SVAE_DTYPE_BF16) {
     if (d->head_dim == 64) { SVAE_FWD(__nv_bfloat16, 64); }

@@ -88,6 +88,60 @@ struct BwdParams {
   float scale, scale_log2;
 };
 
+// ---- per-slot CUDA-core work on one row's 32 scores held in registers --------------------------------------
+__device__ __forceinline__ void mask_above_diag(uint32_t (&v)[32], uint32_t below_diag) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (!((below_diag >> c) & 1u)) v[c] = 0xff800000u;      // -inf
+}
+
+// running max; fast path: raw scores (scaled once at the end), mask path: log2-domain with the additive mask
+__device__ __forceinline__ float slot_max(const uint32_t (&v)[32], float m, bool has_kpm, const float* kp, float scale_log2) {
+  if (!has_kpm) {
+    float a = m, b = -INFINITY, c = -INFINITY, d = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      a = ptx::fmax3(a, __uint_as_float(v[i + 0]), __uint_as_float(v[i + 1]));
+      b = ptx::fmax3(b, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+      c = ptx::fmax3(c, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+      d = ptx::fmax3(d, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+    }
+    return ptx::fmax3(fmaxf(a, b), c, d);
+  }
+  float a0 = m, a1 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    a0 = fmaxf(a0, fmaf(__uint_as_float(v[c]), scale_log2, kp[c]));
+    a1 = fmaxf(a1, fmaf(__uint_as_float(v[c + 1]), scale_log2, kp[c + 1]));
+  }
+  return fmaxf(a0, a1);
+}
+
+template <typename T>
+__device__ __forceinline__ void slot_exp_pack(const uint32_t (&v)[32], uint32_t (&pk)[16], float& l0, float& l1, bool has_kpm,
+                                              const float* kp, float scale_log2, float neg_m) {
+  if (!has_kpm) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), scale_log2, neg_m));
+      const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), scale_log2, neg_m));
+      l0 += p0;
+      l1 += p1;
+      pk[c >> 1] = Elem<T>::pack(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), scale_log2, kp[c]) + neg_m);
+      const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), scale_log2, kp[c + 1]) + neg_m);
+      l0 += p0;
+      l1 += p1;
+      pk[c >> 1] = Elem<T>::pack(p0, p1);
+    }
+  }
+}
+
+
 int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int Dh, int L, int H, int B,
                 const int64_t stride[3], int box_rows);
 

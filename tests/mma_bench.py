@@ -11,7 +11,8 @@ out = torch.zeros(4, dtype=torch.int64, device='cuda')
 count = 64
 print(f'{count} back-to-back MMAs, M=128 K=16: cycles per MMA (issue | issue+drain)')
 for variant, name in ((0, 'SS K-major B'), (2, 'SS MN-major B'), (1, 'TS K-major B'), (3, 'TS MN-major B'),
-                      (4, 'SS, two warps'), (7, 'TS MN, two warps')):
+                      (4, 'SS, two warps'), (7, 'TS MN, two warps'), (8, 'SS conv'), (9, 'TS conv'),
+                      (11, 'TS MN conv'), (12, 'SS conv two warps'), (15, 'TS MN conv two')):
     for n in (32, 64, 96, 128, 256):
         for _ in range(2):
             out.zero_()
