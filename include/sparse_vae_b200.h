@@ -17,6 +17,8 @@
  *   svae_bottleneck_*  ConditionalGaussian.forward                  sparse_vae/core/conditional_gaussian.py:18-30
  *                      + ContinuousVAE.sample_z                     sparse_vae/core/continuous_autoencoder.py:42-52
  *                      + torch.distributions.Normal.rsample (Philox stream of at::native normal_)
+ *   svae_radam_step    RAdam.step                                   sparse_vae/core/rectified_adam.py:15-88
+ *   svae_clip_grad_norm  LanguageModel.on_after_backward            sparse_vae/core/language_model.py:120-122
  * There is no CPU implementation behind this ABI: host pointers are rejected by the host-side wrappers
  * and the library needs an sm_100a device.
  */
@@ -147,6 +149,37 @@ SVAE_API int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dtype
                         int32_t sm_count, int32_t max_threads_per_sm,
                         const float* dz, const float* dsigma, const float* dkl_elem, const float* draw_kl,
                         const float* dkl, void* d_mulogvar, int64_t ld_out, void* stream);
+
+/* ---- optimizer step of the data-parallel trainer ------------------------------ */
+/* Tensor lists are HOST arrays of n device pointers (fp32 tensors, contiguous) with numel[n] element counts. */
+/* number of 65536-element chunks the list splits into = floats of `partials` svae_clip_grad_norm needs */
+SVAE_API int64_t svae_multi_tensor_chunks(int32_t n, const int64_t* numel);
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) as called by LanguageModel.on_after_backward
+ * (sparse_vae/core/language_model.py:120-122): norm_coef[0] = || all grads ||_2, norm_coef[1] =
+ * min(1, max_norm / (norm + 1e-6)), every gradient multiplied in place by norm_coef[1].  Deterministic
+ * (two-level fixed-order reduction through `partials`, device scratch of partials_len floats). */
+SVAE_API int svae_clip_grad_norm(int32_t n, void* const* grads, const int64_t* numel, float max_norm, float* partials,
+                        int64_t partials_len, float* norm_coef, void* stream);
+/* One RAdam step (lamb=False) over all tensors, sparse_vae/core/rectified_adam.py:15-88: `step` is the
+ * group's 1-indexed step counter, lr the group's current learning rate (before rectification).  Scalars are
+ * doubles: the schedule is evaluated in double precision like the reference's Python arithmetic. */
+SVAE_API int svae_radam_step(int32_t n, void* const* params, void* const* grads, void* const* exp_avg,
+                    void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int64_t step, void* stream);
+
+/* ---- LayerNorm of the pre-LN decoder blocks (reference core/transformer_layer.py:17-24) ---- */
+/* x: [rows, n] contiguous (x_dtype), n in {128, 256, 512, 1024}; gamma/beta fp32 [n] (beta may be NULL).
+ * y = (x - mean) * rstd * gamma + beta written in y_dtype (fp32 statistics; a 16-bit y equals the rounded fp32
+ * result, i.e. what autocast's cast in front of the consuming Linear produces); mean, rstd: fp32 [rows]. */
+SVAE_API int svae_layernorm_supported(int32_t n);
+SVAE_API int svae_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, int64_t rows,
+                       int32_t n, float eps, void* y, int32_t y_dtype, float* mean, float* rstd, void* stream);
+SVAE_API int64_t svae_layernorm_bwd_workspace_floats(int64_t rows, int32_t n);
+/* dx (x_dtype, may be NULL), dgamma / dbeta (fp32 [n], may be NULL) from dy (y_dtype) in ONE pass over x and dy;
+ * workspace: device scratch of svae_layernorm_bwd_workspace_floats(rows, n) floats (deterministic two-level sum). */
+SVAE_API int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, int32_t x_dtype, const float* gamma,
+                       const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, float* dgamma,
+                       float* dbeta, float* workspace, int64_t workspace_floats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,8 @@ EXPORTS = (
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench',
+    'svae_multi_tensor_chunks', 'svae_clip_grad_norm', 'svae_radam_step',
+    'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
 )
 
 
@@ -85,6 +87,20 @@ def _load() -> C.CDLL:
     lib.svae_profile_end.argtypes = [C.c_char_p, C.c_size_t]
     lib.svae_debug_mma_bench.restype = C.c_int
     lib.svae_debug_mma_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.svae_multi_tensor_chunks.restype = i64
+    lib.svae_multi_tensor_chunks.argtypes = [i32, vp]
+    lib.svae_clip_grad_norm.restype = C.c_int
+    lib.svae_clip_grad_norm.argtypes = [i32, vp, vp, C.c_float, vp, i64, vp, vp]
+    lib.svae_radam_step.restype = C.c_int
+    lib.svae_radam_step.argtypes = [i32, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp]
+    lib.svae_layernorm_supported.restype = C.c_int
+    lib.svae_layernorm_supported.argtypes = [i32]
+    lib.svae_layernorm_fwd.restype = C.c_int
+    lib.svae_layernorm_fwd.argtypes = [vp, i32, vp, vp, i64, i32, C.c_float, vp, i32, vp, vp, vp]
+    lib.svae_layernorm_bwd_workspace_floats.restype = i64
+    lib.svae_layernorm_bwd_workspace_floats.argtypes = [i64, i32]
+    lib.svae_layernorm_bwd.restype = C.c_int
+    lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, i64, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib

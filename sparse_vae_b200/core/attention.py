@@ -17,6 +17,7 @@ from typing import Optional, Set, Tuple, Union
 import torch
 from torch import nn, Tensor
 
+from .layer_norm import LayerNorm
 from .padded_tensor import PaddedTensor, split_padding
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
@@ -167,8 +168,8 @@ class TransformerLayer(nn.Module):
         self.attention = Attention(d_model, num_heads, causal, learned_queries=learned_queries, sparse=sparse_self_attention)
         self.ffn = nn.Sequential(nn.Linear(d_model, d_model * 4), nn.GELU(), nn.Linear(d_model * 4, d_model, bias=False))
         self.dropout = nn.Dropout(p=0.1)
-        self.attn_layer_norm = nn.LayerNorm(d_model)
-        self.ffn_layer_norm = nn.LayerNorm(d_model)
+        self.attn_layer_norm = LayerNorm(d_model)
+        self.ffn_layer_norm = LayerNorm(d_model)
         self.use_cross_attention = use_cross_attention
 
     @property
@@ -180,8 +181,8 @@ class TransformerLayer(nn.Module):
         if value:
             base = self.attention
             self.cross_attention = Attention(d_model=base.d_model, num_heads=base.num_heads)
-            self.cross_attn_layer_norm = nn.LayerNorm(base.d_model)
-            self.context_layer_norm = nn.LayerNorm(base.d_model)
+            self.cross_attn_layer_norm = LayerNorm(base.d_model)
+            self.context_layer_norm = LayerNorm(base.d_model)
         else:
             self.cross_attention = None
 

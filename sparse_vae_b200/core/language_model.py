@@ -92,7 +92,15 @@ class LanguageModel(LightningModule, ABC):
         return self.get_nll(logits, batch['token_ids'][..., 1:].long())
 
     def on_after_backward(self):
-        grad_norm = torch.nn.utils.clip_grad_norm_(self.parameters(), self.hparams.grad_clip_threshold)
+        grads = [p.grad for p in self.parameters() if p.grad is not None]
+        if grads and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in grads):
+            # one fused multi-tensor pass (csrc/optim.cu) instead of a per-parameter norm + scale
+            if getattr(self, '_fused_clipper', None) is None:
+                from ..fused_optim import FusedGradClipper
+                self._fused_clipper = FusedGradClipper()
+            grad_norm = self._fused_clipper(grads, self.hparams.grad_clip_threshold)
+        else:
+            grad_norm = torch.nn.utils.clip_grad_norm_(self.parameters(), self.hparams.grad_clip_threshold)
         self.log('grad_norm', grad_norm, on_step=True)
 
     def validation_step(self, batch: Dict[str, Tensor], batch_index: int) -> Tensor:

@@ -1,0 +1,76 @@
+"""`LayerNorm`: drop-in subclass of `nn.LayerNorm` (same parameters / state_dict keys) backed by the one-pass
+sm_100a kernels of csrc/layernorm.cu.  Used by `TransformerLayer` (reference core/transformer_layer.py:17-24:
+`attn_layer_norm`, `ffn_layer_norm`, ...) and the output head (core/transformer_language_model.py:55-63).
+
+Arithmetic is the reference's: fp32 statistics and affine transform.  Under autocast the reference's LayerNorm
+returns fp32 and each consuming `nn.Linear` casts that to the autocast dtype; every LayerNorm of the model feeds
+only Linear layers, so this module writes the rounded 16-bit result directly (`emit_autocast_dtype=True`) -- the
+values the Linear layers see are bit-identical, the three per-consumer casts and the fp32 round trip disappear.
+(The only numerical difference: gradients of several consumers are summed in the 16-bit dtype before the
+LayerNorm backward instead of in fp32.)  Shapes / dtypes the kernels do not cover use ATen's `F.layer_norm`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn, Tensor
+
+from .. import _native as N
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias, eps: float, out_dtype: torch.dtype):
+        n = x.shape[-1]
+        x2 = x.reshape(-1, n)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        y = torch.empty((rows, n), device=x.device, dtype=out_dtype)
+        stats = torch.empty((2, rows), device=x.device, dtype=torch.float32)
+        N.check(N.lib.svae_layernorm_fwd(x2.data_ptr(), N.svae_dtype(x2.dtype), weight.data_ptr(), N.ptr(bias), rows, n,
+                                         float(eps), y.data_ptr(), N.svae_dtype(out_dtype), stats[0].data_ptr(),
+                                         stats[1].data_ptr(), N.current_stream(x.device)), 'svae_layernorm_fwd')
+        ctx.save_for_backward(x2, weight, stats)
+        ctx.has_bias = bias is not None
+        ctx.x_shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, weight, stats = ctx.saved_tensors
+        rows, n = x2.shape
+        dy2 = dy.reshape(rows, n)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x2) if need_x else None
+        dgb = torch.empty((2, n), device=x2.device, dtype=torch.float32) if (need_w or need_b) else None
+        ws_floats = N.lib.svae_layernorm_bwd_workspace_floats(rows, n)
+        ws = torch.empty(ws_floats, device=x2.device, dtype=torch.float32)
+        N.check(N.lib.svae_layernorm_bwd(dy2.data_ptr(), N.svae_dtype(dy2.dtype), x2.data_ptr(), N.svae_dtype(x2.dtype),
+                                         weight.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), rows, n, N.ptr(dx),
+                                         dgb[0].data_ptr() if need_w else None, dgb[1].data_ptr() if need_b else None,
+                                         ws.data_ptr(), ws_floats, N.current_stream(x2.device)), 'svae_layernorm_bwd')
+        return (dx.view(ctx.x_shape) if need_x else None, dgb[0] if need_w else None, dgb[1] if need_b else None,
+                None, None)
+
+
+_PAIRS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.float32, torch.float16),
+          (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32), (torch.float16, torch.float16),
+          (torch.float16, torch.float32)}
+
+
+class LayerNorm(nn.LayerNorm):
+    emit_autocast_dtype: bool = True
+
+    def forward(self, x: Tensor) -> Tensor:
+        fused = (x.is_cuda and self.elementwise_affine and len(self.normalized_shape) == 1 and x.numel() > 0
+                 and self.weight.dtype == torch.float32 and N.lib.svae_layernorm_supported(x.shape[-1]))
+        if fused:
+            out_dtype = x.dtype
+            if torch.is_autocast_enabled('cuda'):
+                out_dtype = torch.get_autocast_dtype('cuda') if self.emit_autocast_dtype else torch.float32
+            if (x.dtype, out_dtype) in _PAIRS:
+                return _LayerNormFn.apply(x, self.weight, self.bias, self.eps, out_dtype)
+        return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)

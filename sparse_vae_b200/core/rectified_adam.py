@@ -1,7 +1,8 @@
 """RAdam with optional LAMB trust ratio (reference surface: sparse_vae/core/rectified_adam.py).
 
 Same hyper-parameters, state names (`exp_avg`, `exp_avg_sq`, per-group 1-indexed `step`) and update rule as the
-reference, evaluated with torch._foreach ops over each parameter group instead of a Python loop per tensor.
+reference.  CUDA fp32 parameter groups (lamb=False) take ONE fused multi-tensor kernel pass (csrc/optim.cu,
+`svae_radam_step`); CPU tensors and LAMB groups are evaluated with torch._foreach ops.
 """
 from __future__ import annotations
 
@@ -52,6 +53,16 @@ class RAdam(Optimizer):
                     state['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 params.append(p); grads.append(p.grad); m.append(state['exp_avg']); v.append(state['exp_avg_sq'])
             if not params:
+                group['step'] += 1
+                continue
+
+            if not group['lamb'] and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+                from ..fused_optim import FusedRAdamStep
+                cache = self.__dict__.setdefault('_fused_steps', {})     # kept off param_groups (state_dict stays clean)
+                fused = cache.get(id(group))
+                if fused is None:
+                    fused = cache[id(group)] = FusedRAdamStep()
+                fused(params, grads, m, v, group['lr'], beta1, beta2, group['eps'], group['weight_decay'], step)
                 group['step'] += 1
                 continue
 
