@@ -181,6 +181,14 @@ SVAE_API int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, 
                        const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, float* dgamma,
                        float* dbeta, float* workspace, int64_t workspace_floats, void* stream);
 
+/* ---- vocabulary cross-entropy (reference core/language_model.py:98-113,161-170) ---- */
+/* logits: [rows, vocab] (dtype), row stride ld elements, vocab = 8192*k (k <= 4).  nll[r] = logsumexp(row) -
+ * row[labels[r]] (fp32); if write_grad, the row is overwritten with weight[r] * (softmax(row) - onehot(labels[r])).
+ * weight[r] == 0 marks an ignored row (nll 0, zero gradient).  One read + one write of the logits. */
+SVAE_API int svae_vocab_ce_supported(int32_t vocab);
+SVAE_API int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t vocab, int64_t ld, const int64_t* labels,
+                  const float* weight, float* nll, int32_t write_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

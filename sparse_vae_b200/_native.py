@@ -27,6 +27,7 @@ EXPORTS = (
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench',
     'svae_multi_tensor_chunks', 'svae_clip_grad_norm', 'svae_radam_step',
+    'svae_vocab_ce_supported', 'svae_vocab_ce',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
 )
 
@@ -101,6 +102,10 @@ def _load() -> C.CDLL:
     lib.svae_layernorm_bwd_workspace_floats.argtypes = [i64, i32]
     lib.svae_layernorm_bwd.restype = C.c_int
     lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, i64, vp]
+    lib.svae_vocab_ce_supported.restype = C.c_int
+    lib.svae_vocab_ce_supported.argtypes = [i32]
+    lib.svae_vocab_ce.restype = C.c_int
+    lib.svae_vocab_ce.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, i32, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib

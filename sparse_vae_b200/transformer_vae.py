@@ -16,6 +16,7 @@ from torch.utils.checkpoint import checkpoint
 from .core.attention import Attention, Perceiver
 from .core.conditional_gaussian import ConditionalGaussian
 from .core.continuous_autoencoder import ContinuousVAE, ContinuousVAEHparams
+from .core import fused_ce
 from .core.generation import GenerationState
 from .core.lightning_shim import DictConfig
 from .core.math_utils import marginal_kl
@@ -52,9 +53,16 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         encoder_out = self.encoder(x, padding=padding)
         z, kl, posterior = self.sample_z(encoder_out, token_counts=batch['num_tokens'], stage=stage)
 
-        logits = self.reconstruct(x, z, padding=padding)[..., :-1, :]
-        nll = self.get_nll(logits, original[..., 1:], stage=stage,
-                           bytes_per_token=batch['num_bytes'] / batch['num_tokens'] if stage == 'val' else None)
+        head = self.output_layer[-1]
+        if fused_ce.supported(x, head) and not (stage == 'val' and hasattr(self, 'token_weights')):
+            # vocabulary projection + cross-entropy without materialising the logits (core/fused_ce.py)
+            hidden = self.reconstruct(x, z, padding=padding, return_hidden=True)
+            nll = fused_ce.fused_vocab_nll(hidden, head, original[..., 1:])
+            self.log(stage + '_nll', nll)
+        else:
+            logits = self.reconstruct(x, z, padding=padding)[..., :-1, :]
+            nll = self.get_nll(logits, original[..., 1:], stage=stage,
+                               bytes_per_token=batch['num_bytes'] / batch['num_tokens'] if stage == 'val' else None)
         loss = nll + self.hparams.kl_weight * kl
 
         if original.shape[0] > 1:
@@ -86,13 +94,15 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         padding = original.eq(0) if padding is None else padding
         return self.q_of_z_given_x(self.encoder(self.input_layer(original), padding=padding), get_kl=False)
 
-    def reconstruct(self, x, z, padding: Optional[Tensor] = None) -> Tensor:
+    def reconstruct(self, x, z, padding: Optional[Tensor] = None, return_hidden: bool = False) -> Tensor:
         x, x_pad = split_padding(x)
         padding = x_pad if padding is None else padding
         use_checkpoint = self.hparams.grad_checkpointing and x.requires_grad
         for layer, project in zip(self.decoder_layers, self.z_projections):
             x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)       # z takes the [CLS] position
             x = checkpoint(layer, x, None, padding, use_reentrant=False) if use_checkpoint else layer(x, padding=padding)
+        if return_hidden:                                   # everything but the vocabulary projection
+            return self.output_layer[:-1](x)
         return self.output_layer(x)
 
     def sample(self, max_length: int, batch_size: int = 1, **kwargs):

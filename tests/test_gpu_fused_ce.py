@@ -1,0 +1,116 @@
+"""Fused vocabulary head + cross-entropy (csrc/vocab_ce.cu, core/fused_ce.py) against the reference's
+`robust_cross_entropy(Linear(hidden)[..., :-1, :], labels)` (core/language_model.py:161-170)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_nll(hidden, weight, bias, labels):
+    """Literal restatement of the reference: full logits, slice, chunked F.cross_entropy(ignore_index=0)."""
+    logits = F.linear(hidden, weight, bias)[..., :-1, :]
+    chunks = -(-logits.numel() // 2 ** 30)
+    if chunks == 1:
+        return F.cross_entropy(logits.flatten(end_dim=1), labels.flatten(), ignore_index=0)
+    return torch.stack([F.cross_entropy(lo.flatten(end_dim=1), la.flatten(), ignore_index=0)
+                        for lo, la in zip(logits.chunk(chunks, dim=-2), labels.chunk(chunks, dim=-1))]).mean()
+
+
+def _setup(B, L, D, V, seed, pad_from=None):
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(B, L, D, generator=g)
+    weight = torch.randn(V, D, generator=g) * 0.05
+    bias = torch.randn(V, generator=g) * 0.1
+    labels = torch.randint(1, V, (B, L - 1), generator=g)
+    if pad_from is not None:
+        for b, p in enumerate(pad_from):
+            labels[b, p:] = 0
+    return hidden, weight, bias, labels
+
+
+@pytest.mark.parametrize('V', [8192, 32768])
+@pytest.mark.parametrize('row_chunk', [4096, 100])
+def test_fused_ce_fp32_matches_float64_reference(V, row_chunk):
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    B, L, D = 3, 130, 64
+    hidden, weight, bias, labels = _setup(B, L, D, V, seed=V + row_chunk, pad_from=[129, 77, 5])
+    hd, wd, bd = (t.double().requires_grad_(True) for t in (hidden, weight, bias))
+    ref = _reference_nll(hd, wd, bd, labels)
+    ref.backward()
+    lin = torch.nn.Linear(D, V).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(weight); lin.bias.copy_(bias)
+    h = hidden.cuda().requires_grad_(True)
+    loss = fused_vocab_nll(h, lin, labels.cuda(), row_chunk=row_chunk)
+    (loss * 1.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    for got, want in ((h.grad, hd.grad), (lin.weight.grad, wd.grad), (lin.bias.grad, bd.grad)):
+        assert (got.double().cpu() - want).abs().max() <= 2e-4 * want.abs().max()     # TF32-free fp32 GEMMs
+    # upstream gradient scaling
+    h2 = hidden.cuda().requires_grad_(True)
+    lin.zero_grad()
+    (fused_vocab_nll(h2, lin, labels.cuda(), row_chunk=row_chunk) * 0.25).backward()
+    torch.testing.assert_close(h2.grad, h.grad * 0.25, rtol=1e-6, atol=1e-9)
+
+
+def test_fused_ce_multi_chunk_weighting_matches_reference():
+    """More than 2**30 logits: the reference averages per-chunk means (chunks of unequal valid-token counts)."""
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    B, L, D, V = 4, 8200, 32, 32768                     # 4 * 8199 * 32768 > 2**30 -> 2 chunks along the sequence
+    hidden, weight, bias, labels = _setup(B, L, D, V, seed=11, pad_from=[8199, 6000, 4100, 300])
+    lin = torch.nn.Linear(D, V).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(weight); lin.bias.copy_(bias)
+    h = hidden.cuda().requires_grad_(True)
+    loss = fused_vocab_nll(h, lin, labels.cuda())
+    loss.backward()
+    h_ref = hidden.cuda().requires_grad_(True)
+    w_ref, b_ref = (t.detach().clone().requires_grad_(True) for t in (lin.weight, lin.bias))
+    ref = _reference_nll(h_ref, w_ref, b_ref, labels.cuda())          # plain ATen ops on the GPU, fp32
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (h.grad - h_ref.grad).abs().max() <= 1e-3 * h_ref.grad.abs().max()
+    assert (lin.weight.grad - w_ref.grad).abs().max() <= 1e-3 * w_ref.grad.abs().max()
+    assert (lin.bias.grad - b_ref.grad).abs().max() <= 1e-3 * b_ref.grad.abs().max()
+
+
+def test_fused_ce_autocast_matches_reference_sequence():
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    B, L, D, V = 2, 513, 512, 32768
+    hidden, weight, bias, labels = _setup(B, L, D, V, seed=5, pad_from=[512, 400])
+    lin = torch.nn.Linear(D, V).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(weight); lin.bias.copy_(bias)
+    h = hidden.cuda().requires_grad_(True)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        loss = fused_vocab_nll(h, lin, labels.cuda())
+    loss.backward()
+    h_ref = hidden.cuda().requires_grad_(True)
+    w_ref, b_ref = (t.detach().clone().requires_grad_(True) for t in (lin.weight, lin.bias))
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        ref = _reference_nll(h_ref, w_ref, b_ref, labels.cuda())
+    ref.backward()
+    assert loss.dtype == torch.float32
+    # same rounded logits; this kernel keeps the log-softmax in fp32 (the reference's torch-1.9 autocast did too),
+    # ATen 2.11 rounds the log-probabilities to bf16 -> agreement to ~1e-5..1e-4 of the mean, not bit for bit
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    assert h.grad.dtype == torch.float32
+    assert (h.grad - h_ref.grad).abs().max() <= 1e-2 * h_ref.grad.abs().max()
+    assert (lin.weight.grad - w_ref.grad).abs().max() <= 1e-2 * w_ref.grad.abs().max()
+    assert (lin.bias.grad - b_ref.grad).abs().max() <= 1e-2 * b_ref.grad.abs().max()
+
+
+def test_fused_ce_all_ignored_is_nan_like_reference():
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    lin = torch.nn.Linear(32, 8192).cuda()
+    h = torch.randn(1, 9, 32, device='cuda')
+    labels = torch.zeros(1, 8, dtype=torch.long, device='cuda')
+    assert torch.isnan(fused_vocab_nll(h, lin, labels))
+    assert torch.isnan(_reference_nll(h, lin.weight, lin.bias, labels))
+
+
+def test_fused_ce_rejects_cpu():
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    with pytest.raises(ValueError):
+        fused_vocab_nll(torch.randn(1, 4, 8), torch.nn.Linear(8, 8192), torch.ones(1, 3, dtype=torch.long))

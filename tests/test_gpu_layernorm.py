@@ -62,7 +62,7 @@ def test_layernorm_autocast_feeds_linear_bit_exact():
     # as an occasional 1-ulp flip, never more
     diff = (h.float() - h_ref.to(torch.bfloat16).float()).abs()
     assert (diff > 0).float().mean() < 2e-3
-    assert (diff <= h_ref.abs() * 2 ** -6).all()
+    assert (diff <= h_ref.abs() * 2 ** -7 + 1e-5).all()      # absolute slack: outputs that cancel to ~0
     assert (out.float() - out_ref.float()).abs().max() <= 2e-2 * out_ref.float().abs().max()
 
 
