@@ -189,6 +189,16 @@ SVAE_API int svae_vocab_ce_supported(int32_t vocab);
 SVAE_API int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t vocab, int64_t ld, const int64_t* labels,
                   const float* weight, float* nll, int32_t write_grad, void* stream);
 
+/* ---- rotary position encoding of q / k (reference core/attention.py:194-208) ---- */
+/* x, out: [rows, d_model] contiguous (dtype), row r sits at position r % seq_len; cos / sin tables: [seq_len,
+ * d_model/2] (table_dtype) built by the caller with the reference's own ops.  Pairs (2i, 2i+1) are rotated.
+ * table_dtype == dtype: one rounding per product and per sum in `dtype` (the reference outside autocast).
+ * table_dtype == F32 with a 16-bit dtype: the reference under autocast (fp32 cos/sin, promoted products): forward
+ * in fp32 rounded once to `dtype`, backward with each product cast to `dtype` before the sum.
+ * conj != 0 rotates by the negative angle (= the backward pass).  x == out is allowed. */
+SVAE_API int svae_rotary(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype,
+                int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ EXPORTS = (
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench',
     'svae_multi_tensor_chunks', 'svae_clip_grad_norm', 'svae_radam_step',
-    'svae_vocab_ce_supported', 'svae_vocab_ce',
+    'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
 )
 
@@ -106,6 +106,8 @@ def _load() -> C.CDLL:
     lib.svae_vocab_ce_supported.argtypes = [i32]
     lib.svae_vocab_ce.restype = C.c_int
     lib.svae_vocab_ce.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, i32, vp]
+    lib.svae_rotary.restype = C.c_int
+    lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib

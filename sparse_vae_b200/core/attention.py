@@ -17,23 +17,78 @@ from typing import Optional, Set, Tuple, Union
 import torch
 from torch import nn, Tensor
 
+from .. import _native as N
 from .layer_norm import LayerNorm
 from .padded_tensor import PaddedTensor, split_padding
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
 
 
+def _rotary_tables(length: int, half: int, start: int, max_pos: int, dtype, device) -> Tuple[Tensor, Tensor]:
+    """cos / sin of pos * max_pos**(-i/half), every intermediate in `dtype` exactly as the reference evaluates it
+    (core/attention.py:196-199: positions, frequencies, angles rounded to the activation dtype)."""
+    freq = torch.arange(half, dtype=dtype, device=device)
+    pos = torch.arange(start, start + length, dtype=dtype, device=device)
+    angle = pos[:, None] * (max_pos ** (-freq / half))
+    return angle.cos(), angle.sin()
+
+
+_TABLE_CACHE: dict = {}
+
+
+def _cached_tables(length, half, start, max_pos, dtype, device):
+    if start != 0:                       # token-by-token decoding: one row, not worth caching
+        return _rotary_tables(length, half, start, max_pos, dtype, device)
+    # under autocast `max_pos ** t` is an fp32 op, so the tables (and the reference's products) are fp32
+    key = (length, half, max_pos, dtype, device, torch.is_autocast_enabled('cuda'))
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        if len(_TABLE_CACHE) >= 16:
+            _TABLE_CACHE.clear()
+        hit = _TABLE_CACHE[key] = tuple(t.contiguous() for t in _rotary_tables(length, half, 0, max_pos, dtype, device))
+    return hit
+
+
+class _RotaryFn(torch.autograd.Function):
+    """One-launch rotation (csrc/rotary.cu), forward and backward bit-identical to the reference's op sequence."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, cos: Tensor, sin: Tensor):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        L, d = x.shape[-2], x.shape[-1]
+        N.check(N.lib.svae_rotary(x.data_ptr(), cos.data_ptr(), sin.data_ptr(), out.data_ptr(), N.svae_dtype(x.dtype),
+                                  N.svae_dtype(cos.dtype), x.numel() // d, L, d, 0, N.current_stream(x.device)), 'svae_rotary')
+        ctx.save_for_backward(cos, sin)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        cos, sin = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(g)
+        L, d = g.shape[-2], g.shape[-1]
+        N.check(N.lib.svae_rotary(g.data_ptr(), cos.data_ptr(), sin.data_ptr(), dx.data_ptr(), N.svae_dtype(g.dtype),
+                                  N.svae_dtype(cos.dtype), g.numel() // d, L, d, 1, N.current_stream(g.device)), 'svae_rotary')
+        return dx, None, None
+
+
 def encode_position_rotary(x: Tensor, start: int = 0, max_pos: int = 10000) -> Tensor:
     """Rotate consecutive feature pairs of x[..., pos, :] by pos * max_pos**(-i/(d/2)).
 
     Evaluated in x.dtype like the reference (core/attention.py:194-208), so low-precision position rounding is
-    reproduced op for op: (x0*cos - x1*sin, x1*cos + x0*sin) with one rounding per product and per sum.
+    reproduced op for op: (x0*cos - x1*sin, x1*cos + x0*sin) with one rounding per product and per sum.  CUDA
+    tensors take the single-launch kernel; the torch expression below is the same arithmetic for CPU tensors.
+    Under autocast the reference's result is fp32 (promoted by the fp32 cos / sin) and every consumer casts it to
+    the autocast dtype at once; the kernel returns that rounded tensor directly.
     """
     half = x.shape[-1] // 2
-    freq = torch.arange(half, dtype=x.dtype, device=x.device)
-    pos = torch.arange(start, start + x.shape[-2], dtype=x.dtype, device=x.device)
-    angle = pos[:, None] * (max_pos ** (-freq / half))
-    cos, sin = angle.cos(), angle.sin()
+    if (x.is_cuda and x.ndim >= 2 and x.shape[-1] % 8 == 0 and x.numel() > 0
+            and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+        cos, sin = _cached_tables(x.shape[-2], half, start, max_pos, x.dtype, x.device)
+        if cos.dtype == x.dtype or cos.dtype == torch.float32:
+            return _RotaryFn.apply(x, cos.contiguous(), sin.contiguous())
+    cos, sin = _rotary_tables(x.shape[-2], half, start, max_pos, x.dtype, x.device)
     pairs = x.unflatten(-1, (half, 2))
     even, odd = pairs[..., 0], pairs[..., 1]
     rotated = torch.stack((even * cos - odd * sin, odd * cos + even * sin), dim=-1)

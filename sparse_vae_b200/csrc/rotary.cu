@@ -1,0 +1,138 @@
+// Rotary position encoding of the q / k projections feeding the sparse-attention kernel, one launch per tensor
+// (reference core/attention.py:194-208 `encode_position_rotary`, called at :61,70).
+//
+// The reference rotates consecutive feature pairs over the FULL d_model before the head split, and evaluates
+// everything in the activation dtype (positions, angles, cos/sin and every product / sum are rounded to bf16 under
+// autocast).  The host side builds the [L, d/2] cos / sin tables with exactly those torch ops; this kernel then
+// applies
+//     out[2i]   = rn(rn(x[2i] * cos_i) - rn(x[2i+1] * sin_i))
+//     out[2i+1] = rn(rn(x[2i+1] * cos_i) + rn(x[2i] * sin_i))
+// with one rounding per product and per sum, i.e. bit-identical to the reference's ~10 element-wise launches on
+// strided views.  `conj = 1` rotates by the negative angle, which is exactly autograd's backward of the above
+// (d even = rn(rn(g_e c) + rn(g_o s)), d odd = rn(rn(g_o c) - rn(g_e s))).
+// HBM-bound: 2 * rows * d * sizeof(T) bytes per launch (tables stay in L2).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace svae {
+
+template <typename T> struct RotOps;
+template <> struct RotOps<float> {
+  using V = float;
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }   // no FMA contraction
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+template <> struct RotOps<__nv_bfloat16> {
+  static __device__ __forceinline__ __nv_bfloat16 mul(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return __float2bfloat16_rn(__bfloat162float(a) * __bfloat162float(b));                    // exact product, one rounding
+  }
+  static __device__ __forceinline__ __nv_bfloat16 add(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return __float2bfloat16_rn(__bfloat162float(a) + __bfloat162float(b));
+  }
+  static __device__ __forceinline__ __nv_bfloat16 sub(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return __float2bfloat16_rn(__bfloat162float(a) - __bfloat162float(b));
+  }
+};
+template <> struct RotOps<__half> {
+  static __device__ __forceinline__ __half mul(__half a, __half b) { return __float2half_rn(__half2float(a) * __half2float(b)); }
+  static __device__ __forceinline__ __half add(__half a, __half b) { return __float2half_rn(__half2float(a) + __half2float(b)); }
+  static __device__ __forceinline__ __half sub(__half a, __half b) { return __float2half_rn(__half2float(a) - __half2float(b)); }
+};
+
+template <typename T, int N> struct alignas(sizeof(T) * N) Pack { T v[N]; };
+
+template <typename T> __device__ __forceinline__ float rot_to_f32(T v);
+template <> __device__ __forceinline__ float rot_to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float rot_to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float rot_to_f32<float>(float v) { return v; }
+
+// one thread = 8 consecutive features (4 pairs) of one row.
+// TT == T : every op rounded to T (the reference outside autocast).
+// TT == float, T 16-bit : the reference UNDER AUTOCAST -- `pow` is an fp32 autocast op, so cos / sin are fp32 and the
+//   products promote to fp32: forward = fp32 products and difference, rounded to T once (the rounding the consuming
+//   matmul's autocast cast applies); backward = autograd of the promoted products: each fp32 product is cast back
+//   to T and the two contributions are summed in T.
+template <typename T, typename TT>
+__global__ void __launch_bounds__(256) rotary_kernel(const T* __restrict__ x, const TT* __restrict__ cos_t,
+                                                      const TT* __restrict__ sin_t, T* __restrict__ out, int64_t rows, int L,
+                                                      int d, int conj) {
+  constexpr bool kMixed = !std::is_same<T, TT>::value;
+  const int vec_per_row = d >> 3;
+  const int64_t total = rows * vec_per_row;
+  const int half = d >> 1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int vcol = (int)(i - r * vec_per_row);
+    const int pos = (int)(r % L);
+    const Pack<T, 8> xv = *reinterpret_cast<const Pack<T, 8>*>(x + r * d + vcol * 8);
+    const Pack<TT, 4> c = *reinterpret_cast<const Pack<TT, 4>*>(cos_t + (int64_t)pos * half + vcol * 4);
+    const Pack<TT, 4> s = *reinterpret_cast<const Pack<TT, 4>*>(sin_t + (int64_t)pos * half + vcol * 4);
+    Pack<T, 8> o;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if constexpr (!kMixed) {
+        const T e = xv.v[2 * p], od = xv.v[2 * p + 1];
+        const T ec = RotOps<T>::mul(e, c.v[p]), os = RotOps<T>::mul(od, s.v[p]);
+        const T oc = RotOps<T>::mul(od, c.v[p]), es = RotOps<T>::mul(e, s.v[p]);
+        if (!conj) {
+          o.v[2 * p] = RotOps<T>::sub(ec, os);
+          o.v[2 * p + 1] = RotOps<T>::add(oc, es);
+        } else {
+          o.v[2 * p] = RotOps<T>::add(ec, os);
+          o.v[2 * p + 1] = RotOps<T>::sub(oc, es);
+        }
+      } else {
+        const float e = rot_to_f32<T>(xv.v[2 * p]), od = rot_to_f32<T>(xv.v[2 * p + 1]);
+        const float cf = c.v[p], sf = s.v[p];
+        const float ec = __fmul_rn(e, cf), os = __fmul_rn(od, sf), oc = __fmul_rn(od, cf), es = __fmul_rn(e, sf);
+        if (!conj) {
+          o.v[2 * p] = from_f32<T>(__fsub_rn(ec, os));
+          o.v[2 * p + 1] = from_f32<T>(__fadd_rn(oc, es));
+        } else {
+          o.v[2 * p] = RotOps<T>::add(from_f32<T>(ec), from_f32<T>(os));
+          o.v[2 * p + 1] = RotOps<T>::sub(from_f32<T>(oc), from_f32<T>(es));
+        }
+      }
+    }
+    *reinterpret_cast<Pack<T, 8>*>(out + r * d + vcol * 8) = o;
+  }
+}
+
+template <typename T, typename TT>
+static int launch_rotary(const void* x, const void* c, const void* s, void* out, int64_t rows, int L, int d, int conj,
+                         cudaStream_t st) {
+  const int64_t total = rows * (d >> 3);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  rotary_kernel<T, TT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const TT*)c, (const TT*)s, (T*)out, rows, L, d, conj);
+  SVAE_CUDA_CHECK(cudaGetLastError());
+  return SVAE_OK;
+}
+
+}  // namespace svae
+
+using namespace svae;
+
+extern "C" int svae_rotary(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype,
+                           int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(x && cos_table && sin_table && out && rows >= 0, SVAE_ERR_INVALID, "svae_rotary: null argument");
+  SVAE_REQUIRE(d_model > 0 && d_model % 8 == 0 && seq_len > 0 && rows % seq_len == 0, SVAE_ERR_INVALID,
+               "svae_rotary: d_model must be a multiple of 8 and rows a multiple of seq_len");
+  SVAE_REQUIRE(table_dtype == dtype || table_dtype == SVAE_DTYPE_F32, SVAE_ERR_INVALID,
+               "svae_rotary: tables must have the tensor's dtype or be fp32 (autocast), got %d / %d", dtype, table_dtype);
+  const uintptr_t xa = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out);
+  const uintptr_t ta = reinterpret_cast<uintptr_t>(cos_table) | reinterpret_cast<uintptr_t>(sin_table);
+  SVAE_REQUIRE((xa & (dtype == SVAE_DTYPE_F32 ? 31 : 15)) == 0 && (ta & (table_dtype == SVAE_DTYPE_F32 ? 15 : 7)) == 0,
+               SVAE_ERR_INVALID, "svae_rotary: misaligned tensor");
+  if (rows == 0) return SVAE_OK;
+  ScopedKernelTimer timer("rotary", st);
+#define SVAE_ROT(T, TT) return launch_rotary<T, TT>(x, cos_table, sin_table, out, rows, seq_len, d_model, conj, st)
+  if (dtype == SVAE_DTYPE_F32) SVAE_ROT(float, float);
+  if (dtype == SVAE_DTYPE_BF16) { if (table_dtype == dtype) SVAE_ROT(__nv_bfloat16, __nv_bfloat16); SVAE_ROT(__nv_bfloat16, float); }
+  if (dtype == SVAE_DTYPE_F16) { if (table_dtype == dtype) SVAE_ROT(__half, __half); SVAE_ROT(__half, float); }
+#undef SVAE_ROT
+  SVAE_REQUIRE(false, SVAE_ERR_INVALID, "svae_rotary: dtype %d", dtype);
+}
