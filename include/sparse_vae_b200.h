@@ -120,6 +120,10 @@ SVAE_API int svae_attn_fwd_debug(const svae_attn_desc* desc, const void* q, cons
  * variant bit 0: A from TMEM, bit 1: B MN-major, bit 2: two issuing warps.  out: int64[4] =
  * {issue, issue+drain} per issuing warp. */
 SVAE_API int svae_debug_mma_bench(int variant, int n, int count, long long* out, void* stream);
+/* Debug micro-benchmark (one CTA, `warps` warps): cycles per warp for `iters` x 8 back-to-back instructions of
+ * mode 0 MUFU.EX2, 1 F2FP bf16x2 pack, 2 FFMA, 3 FMNMX3, 4 tcgen05.ld 32x32b.x32, 5 tcgen05.st 32x32b.x16,
+ * 6 the softmax step (FFMA, EX2, FADD, pack).  out: int64[64]. */
+SVAE_API int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out, void* stream);
 
 /* ---- latent bottleneck ---------------------------------------------------------------------- */
 #define SVAE_BOTTLENECK_WORKSPACE_BYTES 8448

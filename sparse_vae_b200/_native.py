@@ -16,6 +16,8 @@ LIB_PATH = _HERE / 'csrc' / 'libsvae_b200.so'
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ATTN_FORCE_EXACT = 1
+ATTN_PERSISTENT = 2
+ATTN_PERSISTENT_DEFAULT = True       # persistent warp-specialised forward (95 us vs 105 us at the C2 shape)
 BOTTLENECK_WORKSPACE_BYTES = 8448
 ABI_VERSION = 1
 
@@ -25,7 +27,7 @@ EXPORTS = (
     'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
-    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench',
+    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench',
     'svae_multi_tensor_chunks', 'svae_clip_grad_norm', 'svae_radam_step',
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
@@ -108,6 +110,8 @@ def _load() -> C.CDLL:
     lib.svae_vocab_ce.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, i32, vp]
     lib.svae_rotary.restype = C.c_int
     lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
+    lib.svae_debug_pipe_bench.restype = C.c_int
+    lib.svae_debug_pipe_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib

@@ -8,6 +8,7 @@ like the reference's `_validate_inputs` (core/sparse_matmul.py:579-603) non-CUDA
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from functools import lru_cache
 from typing import ClassVar, Optional
@@ -36,6 +37,11 @@ def _new_blhd(B, H, L, Dh, like: torch.Tensor) -> torch.Tensor:
     """[B,H,L,Dh] view of a fresh [B,L,H,Dh] buffer: the caller's `h l d -> l (h d)` rearrange becomes a view
     (the reference pays a copy there, core/attention.py:102)."""
     return torch.empty(B, L, H, Dh, dtype=like.dtype, device=like.device).permute(0, 2, 1, 3)
+
+
+def _env_flag(name: str, default: bool) -> bool:
+    v = os.environ.get(name)
+    return default if v is None else v not in ('0', '', 'false', 'False')
 
 
 def _make_desc(cfg: 'SparseAttention', q, k, v, out, flags=0, scale=None) -> N.AttnDesc:
@@ -141,7 +147,10 @@ class SparseAttention:
                 kpm = kpm.expand(q.shape[0], seq_len).contiguous()
             if kpm.shape[0] != q.shape[0]:
                 raise ValueError(f"key_padding_mask has batch {kpm.shape[0]}, inputs have {q.shape[0]}")
-        out = _SparseAttentionFn.apply(q, k, v, kpm, self, N.ATTN_FORCE_EXACT if force_exact else 0)
+        flags = N.ATTN_FORCE_EXACT if force_exact else 0
+        if _env_flag('SVAE_ATTN_PERSISTENT', N.ATTN_PERSISTENT_DEFAULT):
+            flags |= N.ATTN_PERSISTENT
+        out = _SparseAttentionFn.apply(q, k, v, kpm, self, flags)
         for _ in range(4 - original_dims):
             out = out.squeeze(0)
         return out

@@ -1,18 +1,21 @@
-// Persistent, warp-specialised variant of the fused block-sparse attention forward (sm_100a), used for the
-// reference's default geometry (<= 8 key slots per 128-query tile, <= 4 live band blocks per block-row).
+// Persistent, warp-specialised fused block-sparse attention forward (sm_100a) for the reference's default geometry
+// (<= 8 key slots per 128-query tile, <= 4 live band blocks per block-row).
 //
-// One CTA per SM walks over query tiles (tile = blockIdx.x + i * gridDim.x) with TWO tiles in flight:
-//   warp  8      TMA producer for Q + K (2-deep ring, refilled as soon as the S = Q K^T MMAs of a tile retire)
-//   warp  9      TMA producer for V     (2-deep ring, refilled when both P V chains of a tile retire)
-//   warp 10      tcgen05.mma issuer: S(i) = Q K^T, then the even-slot half of O(i-1) = P V
-//   warps 0-3    softmax group 0 (tiles 0, 2, 4, ...), warps 4-7: softmax group 1 (tiles 1, 3, ...): one batch of
-//                tcgen05.ld of the block-row's live slots, register-resident two-pass softmax, P written over S,
-//                warp 0 of the group issues the odd-slot half of P V, epilogue (O_even + O_odd) / l -> SMEM -> TMA store
-// TMEM: 2 x 256 columns (per tile: S 256 | P aliases 0-127 | O_even 128-191 | O_odd 192-255).
-// Registers are rebalanced with setmaxnreg (softmax warpgroups 232, producer/MMA warpgroup 40) so the 160 live
-// scores of a row stay in registers.  While group 0 runs the CUDA-core softmax of tile i, the tensor pipe computes
-// S(i+1) and the TMA engine is already fetching tile i+2: load latency, MMA and softmax of different tiles overlap
-// inside one SM without relying on a second resident CTA.  Same arithmetic as attn_fwd_sm100_kernel.
+// One CTA per SM walks over query tiles (tile = blockIdx.x + i * gridDim.x), two tiles in TMEM at any time and a
+// third in its epilogue, 16 warps:
+//   warps 0-3   softmax group 0 (tiles 0, 2, ...)  | one batch of tcgen05.ld of the block-row's live slots, two-pass
+//   warps 4-7   softmax group 1 (tiles 1, 3, ...)  | register-resident softmax, P written over S in TMEM, LSE
+//   warps 8-11  epilogue group (every tile): (O_even + O_odd) / l -> 16-bit -> swizzled SMEM -> TMA store; frees TMEM
+//   warp 12     TMA producer: Q + K (2-deep ring, refilled when the tile's S = Q K^T MMAs retire) and V (2-deep ring,
+//               refilled when both P V chains retire)
+//   warp 13     tcgen05.mma issuer: S(i) = Q K^T (never blocks on another tile's softmax)
+//   warp 14/15  tcgen05.mma issuers: the even- / odd-slot half of O(i) = P V
+// TMEM: 2 x 256 columns (per tile: S 256 | P aliases 0-127 | O_even 128-191 | O_odd 192-255).  Registers are
+// rebalanced with setmaxnreg (softmax 184, epilogue 88, producers 40).  While group 0 runs the CUDA-core softmax of
+// tile i, group 1 works on tile i+1, the epilogue group drains tile i-1, the tensor pipe computes the next S and the
+// TMA engine is already fetching tile i+2.  Same arithmetic as attn_fwd_sm100_kernel.
+#include <stdlib.h>
+
 #include "attn_sm100.cuh"
 
 namespace svae {
@@ -20,7 +23,7 @@ namespace sm100 {
 
 using namespace ptx;
 
-constexpr int kPersistThreads = 384;     // 3 warpgroups: softmax 0, softmax 1, {TMA QK, TMA V, MMA, spare}
+constexpr int kPersistThreads = 512;
 
 template <int DH>
 struct FwdPSmem {
@@ -34,7 +37,8 @@ struct FwdPSmem {
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;         // [2]
   static constexpr int OFF_OST = OFF_V + 2 * KV_BYTES;       // [2] output staging
   static constexpr int OFF_KPM = OFF_OST + 2 * Q_BYTES;      // [2]
-  static constexpr int OFF_BAR = OFF_KPM + 2 * NS * kBlock * 4;
+  static constexpr int OFF_INV = OFF_KPM + 2 * NS * kBlock * 4;   // [2][128] 1 / row sum, softmax -> epilogue
+  static constexpr int OFF_BAR = OFF_INV + 2 * kTile * 4;
   static constexpr int DYN_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int O_COL = 128, O2_COL = 192;
   static_assert(DYN_BYTES <= 227 * 1024, "shared memory");
@@ -52,19 +56,27 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* qk_full = bars + 0;     // [2] TMA -> MMA
-  uint64_t* v_full = bars + 2;      // [2] TMA -> MMA / chain-B warp
-  uint64_t* qk_free = bars + 4;     // [2] MMA (S retired) -> Q/K producer
-  uint64_t* v_free = bars + 6;      // [2] both P V chains retired -> V producer            (2 arrivals)
+  uint64_t* v_full = bars + 2;      // [2] TMA -> the two P V issuers
+  uint64_t* qk_free = bars + 4;     // [2] S retired -> Q/K producer
+  uint64_t* v_free = bars + 6;      // [2] both P V chains retired -> V producer              (2 arrivals)
   uint64_t* s_ready = bars + 8;     // [2] MMA -> softmax group
-  uint64_t* p_ready = bars + 10;    // [2] softmax group -> MMA / chain-B warp              (128 arrivals)
-  uint64_t* o_ready = bars + 12;    // [2] both P V chains retired -> softmax group          (2 arrivals)
-  uint64_t* tmem_free = bars + 14;  // [2] group has read O: TMEM half reusable              (128 arrivals)
+  uint64_t* p_ready = bars + 10;    // [2] softmax group -> the two P V issuers                (128 arrivals)
+  uint64_t* o_ready = bars + 12;    // [2] both P V chains retired -> epilogue group           (2 arrivals)
+  uint64_t* tmem_free = bars + 14;  // [2] epilogue has read O: TMEM half reusable             (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const TileGeom g = p.g;
   const int ns = g.nslots;
   const int nt = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
+  if (p.timeline && threadIdx.x == 0) {          // debug: CTA start (role 1 of its first tile): clock, globaltimer, SM id
+    long long* tl = p.timeline + ((int64_t)blockIdx.x * 5 + 1) * 8;
+    unsigned smid;
+    unsigned long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tl[0] = clock64(); tl[1] = (long long)gt; tl[2] = smid;
+  }
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < 2; ++k) {
@@ -73,7 +85,7 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     }
     fence_barrier_init();
   }
-  if (warp == 11) {
+  if (warp == 15) {
     if (lane == 0) {
       prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV);
       prefetch_tensormap(&tmKband); prefetch_tensormap(&tmVband); prefetch_tensormap(&tmO);
@@ -92,6 +104,9 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     h = bh % p.H;
     b = bh / p.H;
   };
+  auto tl_ptr = [&](int i, int role) -> long long* {
+    return (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + role) * 8 : nullptr;
+  };
   const uint32_t idesc_pv = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
   // O (+)= P_j V_j for slots j = first, first + 2, ... of the tile in ring slot k
   auto issue_pv_chain = [&](int k, int first, uint32_t o_col) {
@@ -108,84 +123,125 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     }
   };
 
-  if (warp >= 8) {
-    // ======================================= producer / MMA warpgroup =======================================
+  if (warp >= 12) {
+    // ======================================= producers / MMA issuers ========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 8) {
+    if (warp == 12) {
+      // ---- TMA producer: Q + K of tile i as soon as S(i-2) has retired, V of tile i as soon as P V(i-2) has retired
       for (int i = 0; i < nt; ++i) {
         const int k = i & 1, n = i >> 1;
         int t, h, b;
         tile_coords(i, t, h, b);
         const int band_lo = 4 * t - (g.left - 1);
-        long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 1) * 8 : nullptr;
-        if (tl) tl[0] = clock64();
         if (i >= 2) mbar_wait(qk_free + k, (n - 1) & 1);
-        if (tl) tl[1] = clock64();
         uint8_t* sQ = smem + S::OFF_Q + k * S::Q_BYTES;
         uint8_t* sK = smem + S::OFF_K + k * S::KV_BYTES;
         mbar_arrive_expect_tx_w(qk_full + k, S::Q_BYTES + ns * S::SLOT_BYTES);
         tma_load_4d_w(sQ, &tmQ, qk_full + k, 0, t * kTile, h, b);
         tma_load_4d_w(sK + g.cls * S::SLOT_BYTES, &tmKband, qk_full + k, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
         if (g.cls) tma_load_4d_w(sK, &tmK, qk_full + k, 0, 0, h, b);
-        if (tl) tl[2] = clock64();
-      }
-    } else if (warp == 9) {
-      for (int i = 0; i < nt; ++i) {
-        const int k = i & 1, n = i >> 1;
-        int t, h, b;
-        tile_coords(i, t, h, b);
-        const int band_lo = 4 * t - (g.left - 1);
-        long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 2) * 8 : nullptr;
-        if (tl) tl[0] = clock64();
         if (i >= 2) mbar_wait(v_free + k, (n - 1) & 1);
-        if (tl) tl[1] = clock64();
         uint8_t* sV = smem + S::OFF_V + k * S::KV_BYTES;
         mbar_arrive_expect_tx_w(v_full + k, ns * S::SLOT_BYTES);
         tma_load_4d_w(sV + g.cls * S::SLOT_BYTES, &tmVband, v_full + k, 0, band_lo * kBlock, h, b);
         if (g.cls) tma_load_4d_w(sV, &tmV, v_full + k, 0, 0, h, b);
-        if (tl) tl[2] = clock64();
       }
-    } else if (warp == 10) {
+    } else if (warp == 13) {
+      // ---- S(i) = Q K^T into TMEM half k; never blocks on the softmax of another tile
       const uint32_t idesc_s = make_idesc(kTile, ns * kBlock, Elem<T>::fmt, 0, 0);
-      for (int i = 0; i <= nt; ++i) {
-        if (i < nt) {
-          // ---- S(i) = Q K^T into TMEM half k
-          const int k = i & 1, n = i >> 1;
-          long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + 4) * 8 : nullptr;
-          if (tl) tl[0] = clock64();
-          mbar_wait(qk_full + k, n & 1);
-          if (tl) tl[1] = clock64();
-          if (i >= 2) mbar_wait(tmem_free + k, (n - 1) & 1);
-          tc_fence_after();
-          const uint32_t q_addr = smem_u32(smem + S::OFF_Q + k * S::Q_BYTES);
-          const uint32_t k_addr = smem_u32(smem + S::OFF_K + k * S::KV_BYTES);
+      for (int i = 0; i < nt; ++i) {
+        const int k = i & 1, n = i >> 1;
+        long long* tl = tl_ptr(i, 4);
+        if (tl) tl[0] = clock64();
+        mbar_wait(qk_full + k, n & 1);
+        if (tl) tl[1] = clock64();
+        if (i >= 2) mbar_wait(tmem_free + k, (n - 1) & 1);
+        if (i == 1 && p.stagger_cycles > 0) {    // start the second softmax group out of phase with the first
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger_cycles) {}
+        }
+        tc_fence_after();
+        if (tl) tl[2] = clock64();
+        const uint32_t q_addr = smem_u32(smem + S::OFF_Q + k * S::Q_BYTES);
+        const uint32_t k_addr = smem_u32(smem + S::OFF_K + k * S::KV_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < DH / 16; ++ks)
-            mma_ss_w(tmem_base + 256 * k, make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB),
-                     make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
-          tc_commit_w(s_ready + k);
-          tc_commit_w(qk_free + k);
-          if (tl) tl[2] = clock64();
-        }
-        if (i >= 1) {
-          // ---- even-slot half of O(i-1) = P V
-          const int k = (i - 1) & 1, n = (i - 1) >> 1;
-          long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)(i - 1) * gridDim.x) * 5 + 4) * 8 : nullptr;
-          if (tl) tl[3] = clock64();
-          mbar_wait(p_ready + k, n & 1);
-          mbar_wait(v_full + k, n & 1);
-          tc_fence_after();
-          if (tl) tl[4] = clock64();
-          issue_pv_chain(k, 0, S::O_COL);
-          tc_commit_w(o_ready + k);
-          tc_commit_w(v_free + k);
-          if (tl) tl[5] = clock64();
-        }
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma_ss_w(tmem_base + 256 * k, make_smem_desc(q_addr + ks * 32, 16, 8 * ROWB, ROWB),
+                   make_smem_desc(k_addr + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit_w(s_ready + k);
+        tc_commit_w(qk_free + k);
+        if (tl) tl[3] = clock64();
+      }
+    } else {
+      // ---- warp 14: even-slot half of O(i) = P V, warp 15: odd-slot half
+      const int first = warp - 14;
+      for (int i = 0; i < nt; ++i) {
+        const int k = i & 1, n = i >> 1;
+        long long* tl = first == 0 ? tl_ptr(i, 4) : nullptr;
+        if (tl) tl[4] = clock64();
+        mbar_wait(p_ready + k, n & 1);
+        mbar_wait(v_full + k, n & 1);
+        tc_fence_after();
+        if (tl) tl[5] = clock64();
+        issue_pv_chain(k, first, first ? S::O2_COL : S::O_COL);
+        tc_commit_w(o_ready + k);
+        tc_commit_w(v_free + k);
+        if (tl) tl[6] = clock64();
       }
     }
+  } else if (warp >= 8) {
+    // ======================================= epilogue group ==================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int w = warp & 3;                    // TMEM lane quarter
+    const int tid_g = threadIdx.x & 127;
+    const int row = w * 32 + lane;
+    for (int i = 0; i < nt; ++i) {
+      const int k = i & 1, n = i >> 1;
+      int t, h, b;
+      tile_coords(i, t, h, b);
+      const uint32_t trow = tmem_base + 256 * k + ((uint32_t)(w * 32) << 16);
+      uint8_t* sOst = smem + S::OFF_OST + k * S::Q_BYTES;
+      const float* sInv = reinterpret_cast<const float*>(smem + S::OFF_INV) + k * kTile;
+      long long* tl = (w == 0) ? tl_ptr(i, 3) : nullptr;
+      if (tl) tl[0] = clock64();
+      mbar_wait(o_ready + k, n & 1);
+      tc_fence_after();
+      if (tl) tl[1] = clock64();
+      const float inv = sInv[row];             // written before the group's p_ready arrival (ordered through the MMA warp)
+      uint32_t oa[32], ob[32];
+      uint32_t pk[DH / 2];
+#pragma unroll
+      for (int half = 0; half < DH / 32; ++half) {
+        tmem_ld32(trow + S::O_COL + 32 * half, oa);
+        tmem_ld32(trow + S::O2_COL + 32 * half, ob);
+        tmem_wait_ld(oa, ob);
+        if (half == DH / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(tmem_free + k);          // S / P / O of this TMEM half are consumed
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c += 2)
+          pk[half * 16 + (c >> 1)] = Elem<T>::pack((__uint_as_float(oa[c]) + __uint_as_float(ob[c])) * inv,
+                                                   (__uint_as_float(oa[c + 1]) + __uint_as_float(ob[c + 1])) * inv);
+      }
+      if (tl) tl[2] = clock64();
+#pragma unroll
+      for (int ch = 0; ch < DH / 8; ++ch)
+        *reinterpret_cast<uint4*>(sOst + swz_off<ROWB>(row, ch)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (tid_g == 0) {
+        tma_store_4d(&tmO, sOst, 0, t * kTile, h, b);
+        tma_store_commit();
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");    // the OTHER staging tile has been read
+      }
+      named_bar_sync(3, 128);                  // nobody writes the other staging tile before its store has read it
+      if (tl) tl[3] = clock64();
+    }
+    if (tid_g == 0) tma_store_wait_all();
   } else {
-    // ======================================= softmax warpgroups =============================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ======================================= softmax groups ==================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     const int grp = warp >> 2;                 // 0 or 1 = ring slot / TMEM half of this group's tiles
     const int w = warp & 3;                    // TMEM lane quarter = block-row inside the tile
     const int tid_g = threadIdx.x & 127;
@@ -193,12 +249,16 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     const uint32_t tb = tmem_base + 256 * grp;
     const uint32_t trow = tb + ((uint32_t)(w * 32) << 16);
     float* sKpm = reinterpret_cast<float*>(smem + S::OFF_KPM) + grp * (S::NS * kBlock);
-    uint8_t* sOst = smem + S::OFF_OST + grp * S::Q_BYTES;
+    float* sInv = reinterpret_cast<float*>(smem + S::OFF_INV) + grp * kTile;
     const uint32_t below_diag = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);   // bit c set <=> key c <= query lane
     const int nlb = g.left + g.nsup;           // live band slots per block-row (<= 4)
     const int first = g.cls + w;
     const int kdiag = g.causal ? g.left - 1 : -1;
 
+    // Ping-pong between the two groups (named barriers 4 / 5, 128 waiting + 128 arriving threads): the MUFU-bound
+    // exp pass of one group never overlaps the other's, which keeps the groups in antiphase -- one runs its
+    // CUDA-core softmax while the other waits for / feeds the tensor pipe.
+    if (p.stagger_cycles >= 0 && grp == 1) named_bar_arrive(4, 256);
     for (int i = grp; i < nt; i += 2) {
       const int n = i >> 1;
       int t, h, b;
@@ -226,34 +286,41 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
           any_kpm |= (kv != 0.f) ? 1u : 0u;
         }
       }
-      const bool has_kpm = bar_red_or(1 + grp, 128, any_kpm);
+      const bool has_kpm = p.kpm ? bar_red_or(1 + grp, 128, any_kpm) : false;
 
       const bool lg = g.cls && r < g.nb;
       bool lv[4];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) lv[kk] = kk < nlb && r < g.nb && slot_valid(first + kk);
 
-      long long* tl = (p.timeline && lane == 0) ? p.timeline + (((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * 5 + w) * 8 : nullptr;
+      long long* tl = (w == 0) ? tl_ptr(i, 0) : nullptr;
       if (tl) tl[0] = clock64();
       mbar_wait(s_ready + grp, n & 1);
       tc_fence_after();
       if (tl) tl[1] = clock64();
-      uint32_t sg[32], s0[32], s1[32], s2[32], s3[32];
-      if (lg) tmem_ld32(trow, sg);
+      // ---- pass 1: row maximum.  The band scores stay in registers for pass 2; the global block is re-read.
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      float m = -INFINITY, l0 = 0.f, l1 = 0.f;
+      const bool g_diag = g.causal && g.cls && r == 0 && lg;      // block-row 0: the global block IS the diagonal
       if (lv[0]) tmem_ld32(trow + 32 * (first + 0), s0);
       if (lv[1]) tmem_ld32(trow + 32 * (first + 1), s1);
       if (lv[2]) tmem_ld32(trow + 32 * (first + 2), s2);
       if (lv[3]) tmem_ld32(trow + 32 * (first + 3), s3);
-      tmem_wait_ld();
-      tmem_dep(sg); tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
+      if (lg) {
+        uint32_t sg[32];
+        tmem_ld32(trow, sg);
+        tmem_wait_ld(sg);                          // waits for every load above as well
+        if (g_diag) mask_above_diag(sg, below_diag);
+        m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
+      } else {
+        tmem_wait_ld();
+      }
+      tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
       if (kdiag == 0 && lv[0]) mask_above_diag(s0, below_diag);
       if (kdiag == 1 && lv[1]) mask_above_diag(s1, below_diag);
       if (kdiag == 2 && lv[2]) mask_above_diag(s2, below_diag);
       if (kdiag == 3 && lv[3]) mask_above_diag(s3, below_diag);
-      if (g.causal && g.cls && r == 0 && lg) mask_above_diag(sg, below_diag);   // block-row 0: the global block IS the diagonal
 
-      float m = -INFINITY, l0 = 0.f, l1 = 0.f;
-      if (lg) m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
       if (lv[0]) m = slot_max(s0, m, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2);
       if (lv[1]) m = slot_max(s1, m, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2);
       if (lv[2]) m = slot_max(s2, m, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2);
@@ -262,12 +329,22 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
       const float neg_m = (m == -INFINITY) ? 0.f : -m;
       if (tl) tl[2] = clock64();
 
+      // ---- pass 2: P = exp2(s * scale_log2 + mask - m), written over S as packed 16-bit
+      if (p.stagger_cycles >= 0) named_bar_sync(4 + grp, 256);
       uint32_t pk[16];
-      if (lg) { slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m); tmem_st16(trow, pk); }
+      if (lg) {
+        uint32_t sg[32];                         // re-read (keeps 32 registers free across the two passes)
+        tmem_ld32(trow, sg);
+        tmem_wait_ld(sg);
+        if (g_diag) mask_above_diag(sg, below_diag);
+        slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m);
+        tmem_st16(trow, pk);
+      }
       if (lv[0]) { slot_exp_pack<T>(s0, pk, l0, l1, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 0), pk); }
       if (lv[1]) { slot_exp_pack<T>(s1, pk, l0, l1, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 1), pk); }
       if (lv[2]) { slot_exp_pack<T>(s2, pk, l0, l1, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 2), pk); }
       if (lv[3]) { slot_exp_pack<T>(s3, pk, l0, l1, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 3), pk); }
+      if (p.stagger_cycles >= 0) named_bar_arrive(4 + (grp ^ 1), 256);
 #pragma unroll
       for (int c = 0; c < 16; ++c) pk[c] = 0u;
       uint32_t live_mask = lg ? 1u : 0u;
@@ -276,71 +353,24 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
       for (int j = 0; j < ns; ++j)              // P = 0 for the slots this block-row does not attend
         if (!((live_mask >> j) & 1u)) tmem_st16(trow + 16 * j, pk);
       const float l = l0 + l1;
+      sInv[row] = 1.0f / l;                     // l == 0 (row with every key masked) -> inf * 0 = NaN, like the reference softmax
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready + grp);
       if (tl) tl[3] = clock64();
-
-      if (w == 0) {
-        // ---- odd-slot half of O = P V, issued here while this warp would otherwise idle until O is ready
-        mbar_wait(p_ready + grp, n & 1);
-        mbar_wait(v_full + grp, n & 1);
-        tc_fence_after();
-        issue_pv_chain(grp, 1, S::O2_COL);
-        tc_commit_w(o_ready + grp);
-        tc_commit_w(v_free + grp);
-      }
-
-      // ---- epilogue: (O_even + O_odd) / l -> 16-bit -> swizzled staging -> TMA store ; LSE
       if (qpos < p.L) p.lse[((int64_t)b * p.H + h) * p.L + qpos] = (m + log2f(l)) * kLn2;
-      const float inv = 1.0f / l;     // l == 0 (row with every key masked) -> NaN, like the reference softmax
-      if (tl) tl[4] = clock64();
-      mbar_wait(o_ready + grp, n & 1);
-      tc_fence_after();
-      if (tl) tl[5] = clock64();
-      uint32_t oa[32], ob[32], oc[32], od[32];
-      tmem_ld32(trow + S::O_COL, oa);
-      tmem_ld32(trow + S::O2_COL, ob);
-      if (DH == 64) {
-        tmem_ld32(trow + S::O_COL + 32, oc);
-        tmem_ld32(trow + S::O2_COL + 32, od);
-      }
-      tmem_wait_ld();
-      tmem_dep(oa); tmem_dep(ob); tmem_dep(oc); tmem_dep(od);
-      tc_fence_before();
-      mbar_arrive(tmem_free + grp);             // S / P / O of this TMEM half are consumed
-#pragma unroll
-      for (int half = 0; half < DH / 32; ++half) {
-        uint32_t (&va)[32] = half ? oc : oa;
-        uint32_t (&vb)[32] = half ? od : ob;
-#pragma unroll
-        for (int cq = 0; cq < 4; ++cq) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (__uint_as_float(va[cq * 8 + e]) + __uint_as_float(vb[cq * 8 + e])) * inv;
-          uint4 wv;
-          wv.x = Elem<T>::pack(f[0], f[1]);
-          wv.y = Elem<T>::pack(f[2], f[3]);
-          wv.z = Elem<T>::pack(f[4], f[5]);
-          wv.w = Elem<T>::pack(f[6], f[7]);
-          *reinterpret_cast<uint4*>(sOst + swz_off<ROWB>(row, half * 4 + cq)) = wv;
-        }
-      }
-      fence_proxy_async();
-      named_bar_sync(1 + grp, 128);
-      if (tid_g == 32) {                        // a lane of warp 1: warp 0 is busy issuing MMAs
-        tma_store_4d(&tmO, sOst, 0, t * kTile, h, b);
-        tma_store_commit();
-        tma_store_wait_read();                  // staging tile reusable
-      }
-      named_bar_sync(1 + grp, 128);             // nobody overwrites the staging tile before the store has read it
-      if (tl) tl[6] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) tmem_dealloc<512>(tmem_base);
+  if (warp == 15) tmem_dealloc<512>(tmem_base);
+  if (p.timeline && threadIdx.x == 0) {          // debug: CTA end (role 2 of its first tile)
+    long long* tl = p.timeline + ((int64_t)blockIdx.x * 5 + 2) * 8;
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tl[0] = clock64(); tl[1] = (long long)gt;
+  }
 }
 
 template <typename T, int DH>
@@ -360,14 +390,22 @@ static int launch_fwd_persist(const svae_attn_desc* d, const TileGeom& g, const 
   p.kpm = kpm; p.lse = lse; p.s_dump = nullptr; p.timeline = timeline;
   p.L = d->seq_len; p.H = d->heads; p.g = g;
   p.scale_log2 = d->scale * kLog2e;
+  {
+    const char* e = getenv("SVAE_FWD_STAGGER");
+    p.stagger_cycles = e ? atoi(e) : -1;       // < 0: no ping-pong between the softmax groups (measured faster)
+  }
   auto kern = attn_fwd_persist_sm100_kernel<T, DH>;
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0, n = 0;
     SVAE_CUDA_CHECK(cudaGetDevice(&dev));
     SVAE_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
     sm_count = n;
+  }
+  static bool configured = false;      // per template instantiation
+  if (!configured) {
+    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+    configured = true;
   }
   const int tiles_per_seq = (d->seq_len + kTile - 1) / kTile;
   const int num_tiles = tiles_per_seq * d->heads * d->batch;

@@ -376,6 +376,7 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
   p.kpm = kpm; p.lse = lse; p.s_dump = s_dump; p.timeline = timeline;
   p.L = d->seq_len; p.H = d->heads; p.g = g;
   p.scale_log2 = d->scale * kLog2e;
+  p.stagger_cycles = 0;
   auto kern = attn_fwd_sm100_kernel<T, DH, NSMAX>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {

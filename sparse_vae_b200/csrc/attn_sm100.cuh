@@ -76,6 +76,7 @@ struct FwdParams {
   int L, H;
   TileGeom g;
   float scale_log2;     // scale * log2(e)
+  int stagger_cycles;   // persistent kernel: delay of the second softmax group's first tile
 };
 
 struct BwdParams {

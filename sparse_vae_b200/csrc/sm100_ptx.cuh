@@ -40,16 +40,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.  Kept inline and
+// minimal (no printf): an out-of-line slow path makes ptxas ignore setmaxnreg and spill the softmax registers.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-      printf("svae: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 2 GHz
   }
 }
 
@@ -243,6 +240,9 @@ __device__ __forceinline__ void tmem_dep(uint32_t (&r)[32]) {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 }  // namespace ptx

@@ -84,6 +84,32 @@ def test_sm100_bf16_lengths(L, Dh):
     run_case(2, 8, L, Dh, torch.bfloat16, lengths=[L, max(1, L - 37)])
 
 
+@pytest.mark.parametrize('persistent', ['0', '1'])
+@pytest.mark.parametrize('B,L,Dh,window,lengths', [
+    (2, 32, 64, 4, None), (2, 160, 64, 4, [160, 123]), (3, 1024, 64, 4, [1024, 700, 33]), (2, 512, 32, 4, [512, 400]),
+    (1, 640, 64, 2, [620]), (5, 4096, 64, 4, None), (40, 512, 64, 4, None), (1, 2048, 64, 3, [2000]),
+])
+def test_sm100_forward_kernel_variants(monkeypatch, persistent, B, L, Dh, window, lengths):
+    """Both forward kernels (one CTA per tile / persistent warp-specialised) against the oracle; more tiles than
+    SMs (B*H*L/128 > 148) exercises the persistent kernel's rings over many iterations."""
+    monkeypatch.setenv('SVAE_ATTN_PERSISTENT', persistent)
+    run_case(B, 8, L, Dh, torch.bfloat16, window=window, lengths=lengths, check_bwd=False, seed=L + B)
+
+
+def test_sm100_forward_kernel_variants_agree_bitwise(monkeypatch):
+    sv = _sv()
+    dev = torch.device('cuda')
+    cfg = sv.SparseAttention()
+    q, k, v = make_qkv(4, 8, 4096, 64, torch.bfloat16, dev, seed=21)
+    pad = make_padding(4, 4096, [4096, 3000, 4096, 77], dev)
+    outs = []
+    for flag in ('0', '1'):
+        monkeypatch.setenv('SVAE_ATTN_PERSISTENT', flag)
+        outs.append(cfg(q, k, v, key_padding_mask=pad * -1e7))
+    a, b = outs
+    assert torch.equal(torch.nan_to_num(a, nan=123.0), torch.nan_to_num(b, nan=123.0))
+
+
 @pytest.mark.parametrize('window,causal,cls', [
     (1, True, True), (2, True, True), (3, True, False), (4, True, False), (4, False, True), (4, False, False),
     (5, False, True), (2, False, False), (6, True, True), (8, True, True), (10, True, True), (8, False, False),

@@ -1,4 +1,4 @@
-"""Per-phase clock64 timeline of the PERSISTENT forward attention kernel at the C2 shape (debug; not a bench)."""
+"""Per-phase clock64 timeline + event timing of the PERSISTENT forward attention kernel at the C2 shape (debug)."""
 import ctypes
 import sys
 from pathlib import Path
@@ -19,52 +19,59 @@ cfg = sv.SparseAttention()
 q, k, v = make_qkv(B, H, L, Dh, torch.bfloat16, dev, seed=3)
 out = _new_blhd(B, H, L, Dh, q)
 lse = torch.empty(B, H, L, device=dev)
-desc = _make_desc(cfg, q, k, v, out, flags=2)   # SVAE_ATTN_PERSISTENT
+flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
 ncta = B * H * (L // 128)
-tl = torch.zeros(ncta, 5, 8, dtype=torch.int64, device=dev)
-for it in range(3):
-    tl.zero_()
+st = torch.cuda.current_stream().cuda_stream
+
+
+def run(flags, tl=None):
+    desc = _make_desc(cfg, q, k, v, out, flags=flags)
     N.check(N.lib.svae_attn_fwd_debug(ctypes.byref(desc), q.data_ptr(), k.data_ptr(), v.data_ptr(), None, out.data_ptr(),
-                                      lse.data_ptr(), None, tl.data_ptr(), torch.cuda.current_stream().cuda_stream), 'dbg')
+                                      lse.data_ptr(), None, None if tl is None else tl.data_ptr(), st), 'dbg')
+
+
+import os
+for name, flags, stag in (('one CTA per tile', 0, 0), ('persistent', 2, -1), ('persistent', 2, 2000), ('persistent', 2, 0)):
+    os.environ['SVAE_FWD_STAGGER'] = str(stag)
+    ts = []
+    for it in range(8):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(flags); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    print(f'{name:>18s} stagger {stag}: us per launch (L2 flushed) {[round(x, 1) for x in ts]}  median {np.median(ts[2:]):.1f}')
+
+tl = torch.zeros(ncta, 5, 8, dtype=torch.int64, device=dev)
+for it in range(2):
+    tl.zero_()
+    flush.zero_()
+    run(2, tl)
     torch.cuda.synchronize()
 t = tl.cpu().numpy()
 G = 148
-names = ['wait S start', 'S ready', 'max done', 'P arrived', 'pre O wait', 'O ready', 'tile done']
-for w in (0, 3):
-    d = np.diff(t[:, w, :7], axis=1)
-    print(f'softmax warp {w}: mean cycles per phase')
-    for i in range(6):
-        print(f'   {names[i]:>14s} -> {names[i + 1]:<14s} mean {d[:, i].mean():8.0f}  p10 {np.percentile(d[:, i], 10):8.0f}  p90 {np.percentile(d[:, i], 90):8.0f}')
-    print(f'   tile total {np.mean(t[:, w, 6] - t[:, w, 0]):8.0f}')
-mn = ['wait QK start', 'QK landed', 'QK issued', 'wait P start', 'P ready', 'PV issued']
-d = np.diff(t[:, 4, :6], axis=1)
-print('MMA warp:')
-for i in range(5):
-    print(f'   {mn[i]:>14s} -> {mn[i + 1]:<14s} mean {d[:, i].mean():8.0f}  p10 {np.percentile(d[:, i], 10):8.0f}  p90 {np.percentile(d[:, i], 90):8.0f}')
-# one CTA's sequence of tiles: steady-state period
-for cta in (0, 77):
-    ids = np.arange(cta, ncta, G)
-    done = t[ids, 0, 6]
-    print(f'CTA {cta}: tiles {len(ids)}, period between consecutive tile completions (cycles):', np.diff(done)[:12].tolist())
-    print('    S-ready times rel:', (t[ids[:8], 0, 1] - t[ids[0], 0, 0]).tolist())
-    print('    QK landed rel   :', (t[ids[:8], 4, 1] - t[ids[0], 0, 0]).tolist())
-    print('    QK wait start   :', (t[ids[:8], 4, 0] - t[ids[0], 0, 0]).tolist())
+start_gt, end_gt = t[:G, 1, 1], t[:G, 2, 1]
+print('globaltimer: kernel span us', (end_gt.max() - start_gt.min()) / 1e3, ' CTA start spread us', (start_gt.max() - start_gt.min()) / 1e3,
+      ' CTA durations us: min', ((end_gt - start_gt) / 1e3).min(), 'max', ((end_gt - start_gt) / 1e3).max(),
+      ' cycles/us', np.median((t[:G, 2, 0] - t[:G, 1, 0]) / ((end_gt - start_gt) / 1e3)))
+dur = (end_gt - start_gt) / 1e3
+print('slowest CTAs:', np.argsort(dur)[-6:].tolist(), 'on SMs', t[np.argsort(dur)[-6:], 1, 2].tolist(), 'fastest:', np.argsort(dur)[:6].tolist(), 'on SMs', t[np.argsort(dur)[:6], 1, 2].tolist())
 
+
+def phases(role, names):
+    d = np.diff(t[:, role, :len(names)], axis=1)
+    for i in range(len(names) - 1):
+        print(f'   {names[i]:>16s} -> {names[i + 1]:<16s} mean {d[:, i].mean():8.0f}  p10 {np.percentile(d[:, i], 10):8.0f}  p90 {np.percentile(d[:, i], 90):8.0f}')
+
+
+print('softmax warp 0 of the tile\'s group:'); phases(0, ['wait S start', 'S ready', 'max done', 'P arrived'])
+print('epilogue warp 8:'); phases(3, ['wait O start', 'O ready', 'O read', 'tile done'])
+print('MMA warp 14:'); phases(4, ['wait QK start', 'QK landed', 'tmem free', 'S issued', 'wait P start', 'P ready', 'PV issued'])
 for cta in (0, 77):
     ids = np.arange(cta, ncta, G)
-    t0 = t[ids[0], 0, 0]
-    print(f'CTA {cta} producers (rel cycles), tiles 0..7:')
-    print('    QK  wait-start:', (t[ids[:8], 1, 0] - t0).tolist())
-    print('    QK  freed     :', (t[ids[:8], 1, 1] - t0).tolist())
-    print('    QK  issued    :', (t[ids[:8], 1, 2] - t0).tolist())
-    print('    QK  landed    :', (t[ids[:8], 4, 1] - t0).tolist())
-    print('    QK  mma issued:', (t[ids[:8], 4, 2] - t0).tolist())
-    print('    S ready (w0)  :', (t[ids[:8], 0, 1] - t0).tolist())
-    print('    V   freed     :', (t[ids[:8], 2, 1] - t0).tolist())
-    print('    V   issued    :', (t[ids[:8], 2, 2] - t0).tolist())
-    print('    P arrived w0  :', (t[ids[:8], 0, 3] - t0).tolist())
-    print('    PV wait start :', (t[ids[:8], 4, 3] - t0).tolist())
-    print('    PV P ready    :', (t[ids[:8], 4, 4] - t0).tolist())
-    print('    PV issued     :', (t[ids[:8], 4, 5] - t0).tolist())
-    print('    O ready (w0)  :', (t[ids[:8], 0, 5] - t0).tolist())
-    print('    tile done (w0):', (t[ids[:8], 0, 6] - t0).tolist())
+    t0 = t[ids[0], 4, 0]
+    print(f'CTA {cta}: {len(ids)} tiles, total {t[ids[-1], 3, 3] - t0} cycles; per-tile completion period:',
+          np.diff(t[ids, 3, 3])[:14].tolist())
+    for nm, role, col in (('QK landed', 4, 1), ('S issued', 4, 3), ('S ready', 0, 1), ('max done', 0, 2), ('P arrived', 0, 3),
+                          ('PV issued', 4, 6), ('O ready', 3, 1), ('O read', 3, 2), ('tile done', 3, 3)):
+        print(f'    {nm:>10s}:', (t[ids[:8], role, col] - t0).tolist())
