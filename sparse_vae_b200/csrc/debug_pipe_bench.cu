@@ -84,6 +84,21 @@ __global__ void __launch_bounds__(512, 1) pipe_bench_kernel(int mode, int iters,
       }
     }
     a[0] += l;
+  } else if (mode == 7) {                // the same step, 96 elements held in registers, fully unrolled (straight-line)
+    float b[96];
+#pragma unroll
+    for (int i = 0; i < 96; ++i) b[i] = seed * (float)(i + 1) + 0.001f * (float)lane;
+    float l0 = 0.f, l1 = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 96; i += 2) {
+        const float p0 = fast_exp2(fmaf(b[i], 0.125f, -1.0f)), p1 = fast_exp2(fmaf(b[i + 1], 0.125f, -1.0f));
+        l0 += p0; l1 += p1;
+        acc ^= Elem<__nv_bfloat16>::pack(p0, p1);
+        b[i] = p0; b[i + 1] = p1;
+      }
+    }
+    a[0] += l0 + l1;
   }
   const long long t1 = clock64();
   float sum = 0.f;
@@ -102,7 +117,7 @@ __global__ void __launch_bounds__(512, 1) pipe_bench_kernel(int mode, int iters,
 extern "C" __attribute__((visibility("default"))) int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out,
                                                                             void* stream) {
   using namespace svae;
-  SVAE_REQUIRE(warps >= 1 && warps <= 16 && mode >= 0 && mode <= 6, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
+  SVAE_REQUIRE(warps >= 1 && warps <= 16 && mode >= 0 && mode <= 7, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
   sm100::pipe_bench_kernel<<<1, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, out, 0.25f);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
