@@ -158,6 +158,10 @@ SVAE_API int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dtype
 /* Tensor lists are HOST arrays of n device pointers (fp32 tensors, contiguous) with numel[n] element counts. */
 /* number of 65536-element chunks the list splits into = floats of `partials` svae_clip_grad_norm needs */
 SVAE_API int64_t svae_multi_tensor_chunks(int32_t n, const int64_t* numel);
+/* dst[i][:] = src[i][:] * scale for every tensor of the list: packs per-parameter gradients into the flat fp32
+ * all-reduce buckets of the data-parallel trainer (and folds the 1/world_size averaging in). */
+SVAE_API int svae_multi_tensor_scale_copy(int32_t n, void* const* dst, void* const* src, const int64_t* numel, float scale,
+                                 void* stream);
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) as called by LanguageModel.on_after_backward
  * (sparse_vae/core/language_model.py:120-122): norm_coef[0] = || all grads ||_2, norm_coef[1] =
  * min(1, max_norm / (norm + 1e-6)), every gradient multiplied in place by norm_coef[1].  Deterministic

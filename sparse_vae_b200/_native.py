@@ -28,7 +28,7 @@ EXPORTS = (
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench',
-    'svae_multi_tensor_chunks', 'svae_clip_grad_norm', 'svae_radam_step',
+    'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
 )
@@ -92,6 +92,8 @@ def _load() -> C.CDLL:
     lib.svae_debug_mma_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     lib.svae_multi_tensor_chunks.restype = i64
     lib.svae_multi_tensor_chunks.argtypes = [i32, vp]
+    lib.svae_multi_tensor_scale_copy.restype = C.c_int
+    lib.svae_multi_tensor_scale_copy.argtypes = [i32, vp, vp, vp, C.c_float, vp]
     lib.svae_clip_grad_norm.restype = C.c_int
     lib.svae_clip_grad_norm.argtypes = [i32, vp, vp, C.c_float, vp, i64, vp, vp]
     lib.svae_radam_step.restype = C.c_int

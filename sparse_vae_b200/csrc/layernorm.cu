@@ -167,15 +167,25 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const 
   }
 }
 
-__global__ void layernorm_param_grad_kernel(const float* __restrict__ partial, int nblocks, int n2, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n2) return;
+// dgamma / dbeta = column sums of the per-CTA partials [nblocks, 2n]; block = 32 columns x 8 row groups, fixed order
+__global__ void __launch_bounds__(256) layernorm_param_grad_kernel(const float* __restrict__ partial, int nblocks, int n2,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * n2 + c];
-  const int n = n2 >> 1;
-  if (c < n) { if (dgamma) dgamma[c] = s; }
-  else if (dbeta) dbeta[c - n] = s;
+  if (c < n2)
+    for (int b = ry; b < nblocks; b += 8) s += partial[(int64_t)b * n2 + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < n2) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    const int n = n2 >> 1;
+    if (c < n) { if (dgamma) dgamma[c] = t; }
+    else if (dbeta) dbeta[c - n] = t;
+  }
 }
 
 static int ln_grid(int64_t rows) {
@@ -260,7 +270,7 @@ extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x
   int rc = run();
   if (rc) return rc;
   if (dgamma || dbeta) {
-    layernorm_param_grad_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(workspace, rows > 0 ? grid : 0, 2 * n, dgamma, dbeta);
+    layernorm_param_grad_kernel<<<(2 * n + 31) / 32, 256, 0, st>>>(workspace, rows > 0 ? grid : 0, 2 * n, dgamma, dbeta);
     SVAE_CUDA_CHECK(cudaGetLastError());
   }
   return SVAE_OK;

@@ -146,6 +146,27 @@ __global__ void __launch_bounds__(kMtThreads) scale_kernel(const __grid_constant
   }
 }
 
+// dst[i] = src[i] * scale over every tensor of the list (gathers per-parameter gradients into a flat all-reduce bucket)
+__global__ void __launch_bounds__(kMtThreads) scale_copy_kernel(const __grid_constant__ MtTable<2> t, float scale) {
+  const int ti = t.block_tensor[blockIdx.x];
+  const int64_t base = (int64_t)t.block_chunk[blockIdx.x] * kMtChunk;
+  const int64_t n = t.numel[ti];
+  float* d = reinterpret_cast<float*>(t.ptr[0][ti]) + base;
+  const float* s = reinterpret_cast<const float*>(t.ptr[1][ti]) + base;
+  const int cnt = (int)((n - base) < kMtChunk ? (n - base) : kMtChunk);
+  if (((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
+    const int n4 = cnt >> 2;
+    for (int i = threadIdx.x; i < n4; i += kMtThreads) {
+      float4 x = ld4(s + 4 * i);
+      x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+      st4(d + 4 * i, x);
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kMtThreads) d[i] = s[i] * scale;
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += kMtThreads) d[i] = s[i] * scale;
+  }
+}
+
 // Walks the tensor list, filling launch tables; calls launch(table, blocks, first_block_index) whenever one is full.
 template <int NPTR, typename Launch>
 static int for_each_table(int n, void* const* const* lists, const int64_t* numel, Launch&& launch) {
@@ -186,6 +207,19 @@ extern "C" int64_t svae_multi_tensor_chunks(int32_t n, const int64_t* numel) {
   for (int i = 0; i < n; ++i)
     if (numel[i] > 0) total += (numel[i] + kMtChunk - 1) / kMtChunk;
   return total;
+}
+
+extern "C" int svae_multi_tensor_scale_copy(int32_t n, void* const* dst, void* const* src, const int64_t* numel, float scale,
+                                           void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(n >= 0 && dst && src && numel, SVAE_ERR_INVALID, "svae_multi_tensor_scale_copy: null argument");
+  void* const* lists[2] = {dst, src};
+  ScopedKernelTimer timer("grad_gather", st);
+  return for_each_table<2>(n, lists, numel, [&](const MtTable<2>& t, int nb, int) -> int {
+    scale_copy_kernel<<<nb, kMtThreads, 0, st>>>(t, scale);
+    SVAE_CUDA_CHECK(cudaGetLastError());
+    return SVAE_OK;
+  });
 }
 
 extern "C" int svae_clip_grad_norm(int32_t n, void* const* grads, const int64_t* numel, float max_norm, float* partials,

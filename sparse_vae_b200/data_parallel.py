@@ -4,9 +4,11 @@ the CPU tests).  The reference has no distributed code of its own (SURVEY.md sec
 the averaged gradient equal to the global-batch gradient because both loss terms are batch means
 (core/continuous_autoencoder.py:47, core/language_model.py:161-170).
 
-`GradientAllReducer` keeps every grad-bearing parameter's `.grad` as a view into a few flat fp32 buckets and
-launches each bucket's asynchronous all-reduce from a post-accumulate hook as soon as its last gradient has been
-written, so communication overlaps the rest of backward.  Parameters that never receive a gradient (the
+`GradientAllReducer` packs the gradients of every grad-bearing parameter into a few flat fp32 buckets (one
+multi-tensor launch per bucket, with the 1/world averaging folded in) from a post-accumulate hook as soon as the
+bucket's last gradient has been written, and launches the bucket's asynchronous all-reduce at once, so
+communication overlaps the rest of backward; afterwards every `.grad` is a view into its bucket.  With one process
+there is nothing to reduce and the gradients stay where autograd put them.  Parameters that never receive a gradient (the
 reference's unused `pos_linear` layers, core/attention.py:39) are discovered on the first step and left out.
 Gradient clipping must run after `finish()`.
 """
@@ -24,12 +26,37 @@ class _Bucket:
         self.params = params
         self.numel = sum(p.numel() for p in params)
         self.flat = torch.zeros(self.numel, device=device, dtype=dtype)
-        off = 0
+        self.views, off = [], 0
         for p in params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.pending = len(params)
         self.work = None
+        self._fused = None
+
+    def gather(self, scale: float):
+        """Packs the gradients autograd left on the parameters into the flat buffer (times `scale`) and re-points
+        every `.grad` at its slice: one multi-tensor launch on CUDA (csrc/optim.cu), plain copies elsewhere."""
+        todo = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        stale = [v for v, p in zip(self.views, self.params) if p.grad is None]
+        if todo:
+            dst, src = [v for v, _ in todo], [g for _, g in todo]
+            fused = self.flat.is_cuda and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in src) \
+                and self.flat.dtype == torch.float32
+            if fused:
+                if self._fused is None:
+                    from .fused_optim import FusedScaleCopy
+                    self._fused = FusedScaleCopy()
+                self._fused(dst, src, scale)
+            else:
+                for v, g in todo:
+                    v.copy_(g)
+                    if scale != 1.0:
+                        v.mul_(scale)
+        for v in stale:                       # a parameter that got no gradient this step contributes zeros
+            v.zero_()
+        for v, p in zip(self.views, self.params):
+            p.grad = v
 
 
 class GradientAllReducer:
@@ -44,6 +71,7 @@ class GradientAllReducer:
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad)
                          for p in module.parameters() if p.requires_grad]
         self._built = False
+        self._reduced_numel = 0
 
     # ---- hooks ----------------------------------------------------------------------------------
     def _on_grad(self, p: nn.Parameter):
@@ -58,9 +86,10 @@ class GradientAllReducer:
             self._launch(b)
 
     def _launch(self, b: _Bucket):
-        if self.world > 1:
-            b.flat.mul_(1.0 / self.world)
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        # gradients arrive as separate tensors (autograd assigns them: `.grad` is None at the start of a step, so
+        # nothing is zero-filled or accumulated); one launch packs the bucket and applies the 1/world averaging
+        b.gather(1.0 / self.world)
+        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _build(self):
         """After the first backward: bucket the parameters that actually got gradients, in the order they became ready."""
@@ -69,6 +98,11 @@ class GradientAllReducer:
             if id(p) not in seen and p.grad is not None:
                 seen.add(id(p))
                 order.append(p)
+        self._reduced_numel = sum(p.numel() for p in order)
+        self._built = True
+        self._ready_order = []
+        if self.world == 1:                   # nothing to reduce: gradients stay where autograd put them
+            return
         cur, cur_bytes = [], 0
         groups = []
         for p in order:
@@ -80,15 +114,10 @@ class GradientAllReducer:
         if cur:
             groups.append(cur)
         for grp in groups:
-            old = [p.grad.detach().clone() for p in grp]
             b = _Bucket(grp, grp[0].device, torch.float32 if grp[0].dtype != torch.float64 else torch.float64)
-            for p, g in zip(grp, old):
-                p.grad.copy_(g)
             for p in grp:
                 self._bucket_of[id(p)] = b
             self.buckets.append(b)
-        self._built = True
-        self._ready_order = []
 
     # ---- per-step API ------------------------------------------------------------------------------
     def finish(self):
@@ -98,21 +127,19 @@ class GradientAllReducer:
             for b in self.buckets:
                 self._launch(b)
         for b in self.buckets:
+            if b.pending > 0 and b.pending < len(b.params) and b.work is None:
+                self._launch(b)               # some parameter of the bucket got no gradient this step
             if b.work is not None:
                 b.work.wait()
                 b.work = None
             b.pending = len(b.params)
 
     def zero_grad(self):
-        if not self._built:
-            self.module.zero_grad(set_to_none=True)
-            return
-        for b in self.buckets:
-            b.flat.zero_()
+        self.module.zero_grad(set_to_none=True)
 
     @property
     def reduced_numel(self) -> int:
-        return sum(b.numel for b in self.buckets)
+        return self._reduced_numel
 
     def remove(self):
         for h in self._handles:

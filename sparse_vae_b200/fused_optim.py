@@ -81,3 +81,19 @@ class FusedRAdamStep:
         N.check(N.lib.svae_radam_step(p.n, p.ptrs, g.ptrs, m.ptrs, v.ptrs, p.numel, float(lr), float(beta1), float(beta2),
                                       float(eps), float(weight_decay), int(step), N.current_stream(dev)),
                 'svae_radam_step')
+
+
+class FusedScaleCopy:
+    """dst[i] = src[i] * scale over two equally shaped lists of CUDA fp32 tensors, a handful of launches in total."""
+
+    def __init__(self):
+        self._d, self._s = _PtrList(), _PtrList()
+
+    def __call__(self, dst: List[Tensor], src: List[Tensor], scale: float = 1.0):
+        if not dst:
+            return
+        _check_fp32_cuda(dst, 'scale_copy dst')
+        _check_fp32_cuda(src, 'scale_copy src')
+        d, s = self._d.update(dst), self._s.update(src)
+        N.check(N.lib.svae_multi_tensor_scale_copy(d.n, d.ptrs, s.ptrs, d.numel, float(scale),
+                                                   N.current_stream(dst[0].device)), 'svae_multi_tensor_scale_copy')

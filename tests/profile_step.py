@@ -39,3 +39,14 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=45, max_name_column_width=70))
+# kernel-level breakdown (device events only), per step
+from collections import defaultdict
+agg = defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        agg[e.name][0] += 1
+        agg[e.name][1] += e.device_time
+tot = sum(v[1] for v in agg.values())
+print(f'KERNELS: {tot / 3e3:.2f} ms of device time per step')
+for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f'{us / 3e3:8.3f} ms/step {n // 3:5d} x {us / n:8.1f} us  {name[:160]}')
