@@ -197,6 +197,14 @@ SVAE_API int svae_vocab_ce_supported(int32_t vocab);
 SVAE_API int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t vocab, int64_t ld, const int64_t* labels,
                   const float* weight, float* nll, int32_t write_grad, void* stream);
 
+/* ---- bias gradient of the decoder blocks' nn.Linear layers (reference core/attention.py:33-39, ------
+ *      core/transformer_layer.py:20-24): out[c] = sum_r x[r, c], fp32 accumulation, deterministic two-stage sum. */
+/* x: [rows, n] (dtype), row stride ld elements, n % 8 == 0; out: fp32 [n];
+ * workspace: device scratch of svae_colsum_workspace_floats(rows, n) floats. */
+SVAE_API int64_t svae_colsum_workspace_floats(int64_t rows, int32_t n);
+SVAE_API int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, int64_t ld, float* out, float* workspace,
+                int64_t workspace_floats, void* stream);
+
 /* ---- rotary position encoding of q / k (reference core/attention.py:194-208) ---- */
 /* x, out: [rows, d_model] contiguous (dtype), row r sits at position r % seq_len; cos / sin tables: [seq_len,
  * d_model/2] (table_dtype) built by the caller with the reference's own ops.  Pairs (2i, 2i+1) are rotated.

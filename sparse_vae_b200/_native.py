@@ -29,7 +29,7 @@ EXPORTS = (
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench',
     'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
-    'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary',
+    'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
 )
 
@@ -110,6 +110,10 @@ def _load() -> C.CDLL:
     lib.svae_vocab_ce_supported.argtypes = [i32]
     lib.svae_vocab_ce.restype = C.c_int
     lib.svae_vocab_ce.argtypes = [vp, i32, i64, i32, i64, vp, vp, vp, i32, vp]
+    lib.svae_colsum_workspace_floats.restype = i64
+    lib.svae_colsum_workspace_floats.argtypes = [i64, i32]
+    lib.svae_colsum.restype = C.c_int
+    lib.svae_colsum.argtypes = [vp, i32, i64, i32, i64, vp, vp, i64, vp]
     lib.svae_rotary.restype = C.c_int
     lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
     lib.svae_debug_pipe_bench.restype = C.c_int

@@ -19,6 +19,7 @@ from torch import nn, Tensor
 
 from .. import _native as N
 from .layer_norm import LayerNorm
+from .linear import Linear
 from .padded_tensor import PaddedTensor, split_padding
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
@@ -109,12 +110,12 @@ class Attention(nn.Module):
         if learned_queries:
             self.learned_queries = nn.Parameter(torch.randn(1, learned_queries, d_model))
         else:
-            self.q_linear = nn.Linear(d_model, d_model)
+            self.q_linear = Linear(d_model, d_model)
             self.learned_queries = None
-        self.k_linear = nn.Linear(d_model, d_model)
-        self.v_linear = nn.Linear(d_model, d_model)
-        self.output_linear = nn.Linear(d_model, d_model)
-        self.pos_linear = nn.Linear(d_model, d_model)      # present (and unused) in the reference; kept for checkpoints
+        self.k_linear = Linear(d_model, d_model)
+        self.v_linear = Linear(d_model, d_model)
+        self.output_linear = Linear(d_model, d_model)
+        self.pos_linear = Linear(d_model, d_model)      # present (and unused) in the reference; kept for checkpoints
 
         self.cache_index = 0
         self.key_cache = None
@@ -221,7 +222,7 @@ class TransformerLayer(nn.Module):
                  sparse_self_attention: Union[bool, int] = False, learned_queries: int = None):
         super().__init__()
         self.attention = Attention(d_model, num_heads, causal, learned_queries=learned_queries, sparse=sparse_self_attention)
-        self.ffn = nn.Sequential(nn.Linear(d_model, d_model * 4), nn.GELU(), nn.Linear(d_model * 4, d_model, bias=False))
+        self.ffn = nn.Sequential(Linear(d_model, d_model * 4), nn.GELU(), nn.Linear(d_model * 4, d_model, bias=False))
         self.dropout = nn.Dropout(p=0.1)
         self.attn_layer_norm = LayerNorm(d_model)
         self.ffn_layer_norm = LayerNorm(d_model)

@@ -55,8 +55,18 @@ class _VocabNLL(torch.autograd.Function):
         any_grad = any(need)
         nll = torch.empty(rows, device=h.device, dtype=torch.float32)
         dh = torch.empty_like(h) if need[0] else None
-        dw = torch.zeros(V, D, device=h.device, dtype=torch.float32) if need[1] else None
-        db = torch.zeros(V, device=h.device, dtype=torch.float32) if need[2] else None
+        # weight AND bias gradient from one GEMM per chunk: dlogits^T @ [h | 1 | 0...] (8 extra columns keep the rows
+        # 16-byte aligned); column D of the product is the bias gradient, so the logits are never re-read for it
+        aug = 8 if need[2] and compute_dtype != torch.float32 else 0
+        if need[1] or need[2]:
+            dwb = torch.zeros(V, D + aug, device=h.device, dtype=torch.float32)
+            if aug:
+                h_aug = torch.zeros(rows, D + aug, device=h.device, dtype=compute_dtype)
+                h_aug[:, :D] = h
+                h_aug[:, D] = 1
+            else:
+                h_aug = h
+        db = torch.zeros(V, device=h.device, dtype=torch.float32) if need[2] and not aug else None
         stream = N.current_stream(h.device)
         dt = N.svae_dtype(compute_dtype)
         for r0 in range(0, rows, row_chunk):
@@ -66,13 +76,16 @@ class _VocabNLL(torch.autograd.Function):
                                         tw[r0:r1].data_ptr(), nll[r0:r1].data_ptr(), int(any_grad), stream), 'svae_vocab_ce')
             if need[0]:
                 torch.mm(logits, w_c, out=dh[r0:r1])
-            if need[1]:
+            if need[1] or aug:
                 if compute_dtype == torch.float32:
-                    dw.addmm_(logits.t(), h[r0:r1])
+                    dwb.addmm_(logits.t(), h_aug[r0:r1])
                 else:
-                    dw.add_(torch.mm(logits.t(), h[r0:r1], out_dtype=torch.float32))
-            if need[2]:
+                    dwb.add_(torch.mm(logits.t(), h_aug[r0:r1], out_dtype=torch.float32))
+            if db is not None:
                 db.add_(logits.sum(0, dtype=torch.float32))
+        dw = dwb[:, :D] if need[1] else None
+        if aug:
+            db = dwb[:, D].contiguous()
         loss = torch.dot(nll, tw)
         ctx.save_for_backward(dh, dw, db)
         ctx.meta = (hidden.shape, hidden.dtype, weight.dtype, bias.dtype if bias is not None else None)

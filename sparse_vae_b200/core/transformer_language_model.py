@@ -14,6 +14,7 @@ from .attention import Attention, TransformerLayer
 from .generation import GenerationState
 from .language_model import LanguageModel, LanguageModelHparams
 from .layer_norm import LayerNorm
+from .linear import Linear
 from .lightning_shim import DictConfig
 from .padded_tensor import PaddedTensor, split_padding
 from .rotary_embedding import RotaryEmbedding
@@ -54,7 +55,7 @@ class TransformerLanguageModel(LanguageModel):
         self.context_layer = deepcopy(self.input_layer) if hp.cross_attention and hp.separate_context_embedding else None
 
         logits = nn.Linear(d_model, VOCAB_SIZE)
-        self.output_layer = nn.Sequential(nn.Linear(d_model, d_model), nn.GELU(), LayerNorm(d_model), logits)
+        self.output_layer = nn.Sequential(Linear(d_model, d_model), nn.GELU(), LayerNorm(d_model), logits)
         if hp.tie_embedding_weights and d_embedding == d_model:
             logits.weight = embedding.weight
 
