@@ -24,6 +24,27 @@ from .core.padded_tensor import PaddedTensor, split_padding
 from .core.transformer_language_model import TransformerHparams, TransformerLanguageModel
 
 
+class _ReplaceFirstPosition(torch.autograd.Function):
+    """`torch.cat([row, x[..., 1:, :]], dim=-2)` evaluated IN PLACE on x (the reference's way of putting the latent
+    at the [CLS] position of every decoder layer, transformer_vae.py:88): identical values, but no copy of the
+    [B, L, d_model] activations in forward and one pass instead of zero-fill + copy in backward.  Only used when x is
+    a temporary nobody else needs (the previous decoder layer's output)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, row: Tensor):
+        ctx.row_dtype = row.dtype
+        x[..., :1, :] = row
+        ctx.mark_dirty(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        g_row = g[..., :1, :].to(ctx.row_dtype, copy=True)
+        gx = g.clone()
+        gx[..., :1, :] = 0
+        return gx, g_row
+
+
 @dataclass
 class TransformerVAEHparams(TransformerHparams, ContinuousVAEHparams):
     latent_depth: int = 64
@@ -98,8 +119,11 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         x, x_pad = split_padding(x)
         padding = x_pad if padding is None else padding
         use_checkpoint = self.hparams.grad_checkpointing and x.requires_grad
-        for layer, project in zip(self.decoder_layers, self.z_projections):
-            x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)       # z takes the [CLS] position
+        for i, (layer, project) in enumerate(zip(self.decoder_layers, self.z_projections)):
+            if i > 0 and x.is_cuda and x.requires_grad and not x.is_leaf and not use_checkpoint:
+                x = _ReplaceFirstPosition.apply(x, project(z).to(x.dtype))       # x is the previous layer's own output
+            else:
+                x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)   # z takes the [CLS] position
             x = checkpoint(layer, x, None, padding, use_reentrant=False) if use_checkpoint else layer(x, padding=padding)
         if return_hidden:                                   # everything but the vocabulary projection
             return self.output_layer[:-1](x)
