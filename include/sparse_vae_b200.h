@@ -116,6 +116,10 @@ SVAE_API int svae_attn_fwd_debug(const svae_attn_desc* desc, const void* q, cons
                         const float* key_padding_mask, void* out, float* lse, float* s_dump,
                         long long* timeline, void* stream);
 
+/* Debug: when non-NULL, the next svae_attn_bwd launches (tcgen05 path) write clock64 phase stamps into
+ * timeline, int64 [2 kernels (dQ pass, dK/dV pass)][num_ctas][3 roles: warp 0, warp 3, MMA warp][16].  Process-global. */
+SVAE_API void svae_debug_set_bwd_timeline(long long* timeline);
+
 /* Debug micro-benchmark (one CTA): clock64 cycles to issue `count` back-to-back tcgen05.mma (M=128, K=16, N=n).
  * variant bit 0: A from TMEM, bit 1: B MN-major, bit 2: two issuing warps.  out: int64[4] =
  * {issue, issue+drain} per issuing warp. */

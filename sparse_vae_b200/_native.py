@@ -27,7 +27,7 @@ EXPORTS = (
     'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
-    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench',
+    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench', 'svae_debug_set_bwd_timeline',
     'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
@@ -116,6 +116,8 @@ def _load() -> C.CDLL:
     lib.svae_colsum.argtypes = [vp, i32, i64, i32, i64, vp, vp, i64, vp]
     lib.svae_rotary.restype = C.c_int
     lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
+    lib.svae_debug_set_bwd_timeline.restype = None
+    lib.svae_debug_set_bwd_timeline.argtypes = [vp]
     lib.svae_debug_pipe_bench.restype = C.c_int
     lib.svae_debug_pipe_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     if lib.svae_abi_version() != ABI_VERSION:

@@ -25,7 +25,12 @@ namespace sm100 {
 
 using namespace ptx;
 
-constexpr int kBwdSlots = 8;   // key slots per query tile (dQ pass); query slots per key tile <= 7
+long long* g_bwd_timeline = nullptr;   // debug only (svae_debug_set_bwd_timeline)
+
+constexpr int kBwdSlots = 8;
+constexpr int kBwdMathWarps = 8;                 // two warps per TMEM lane quarter: each owns 16 of a slot's 32 columns
+constexpr int kBwdThreads = (kBwdMathWarps + 1) * 32;   // + one TMA / MMA-issue warp
+   // key slots per query tile (dQ pass); query slots per key tile <= 7
 
 // ------------------------------------------------------------------------------------------ dQ pass
 template <int DH>
@@ -47,7 +52,7 @@ struct DqSmem {
 };
 
 template <typename T, int DH>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKband,
@@ -72,6 +77,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const TileGeom g = p.g;
   const int ns = g.nslots;
   const int npass = (ns + PASS - 1) / PASS;
+  long long* tl = nullptr;
+  if (p.timeline && lane == 0 && (warp == 0 || warp == 3 || warp == kBwdMathWarps))
+    tl = p.timeline + ((((int64_t)b * gridDim.y + h) * gridDim.x + t) * 3 + (warp == 0 ? 0 : warp == 3 ? 1 : 2)) * 16;
+  auto stamp = [&](int k) { if (tl) tl[k] = clock64(); };
+  stamp(0);
   const int r0 = 4 * t;
   const int band_lo = r0 - (g.left - 1);
   // SMEM slot order = processing order: band slots 0 .. nband-1, then the global block (slot nband), so that the
@@ -89,10 +99,10 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (smem_u32(smem) & 1023u) { printf("svae: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
     mbar_init(bar_ld, 1);
     mbar_init(bar_dq, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, 128); }
+    for (int i = 0; i < 3; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, kBwdMathWarps * 32); }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kBwdMathWarps) {
     if (lane == 0) {
       prefetch_tensormap(&tmQ); prefetch_tensormap(&tmDO); prefetch_tensormap(&tmO); prefetch_tensormap(&tmK);
       prefetch_tensormap(&tmV); prefetch_tensormap(&tmKband); prefetch_tensormap(&tmVband); prefetch_tensormap(&tmDQ);
@@ -103,8 +113,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  stamp(1);
 
-  if (warp == 4) {
+  if (warp == kBwdMathWarps) {
     {   // the whole warp runs the issue path convergently; one lane is elected inside each wrapper
       mbar_arrive_expect_tx_w(bar_ld, 3 * S::TILE_BYTES + 2 * ns * S::SLOT_BYTES);
       tma_load_4d_w(sQ, &tmQ, bar_ld, 0, t * kTile, h, b);
@@ -133,14 +144,17 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       };
 
+      stamp(2);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
+      stamp(3);
       issue_s_dp(0);
       tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_ds + c, 0);
         tc_fence_after();
+        stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {     // dQ += dS_j K_j
           const int j = order(c * PASS + i);
           if (!slot_valid(j)) continue;
@@ -166,28 +180,32 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
           tc_commit_w(bar_dq);
         }
+        stamp(5 + 2 * c);
       }
     }
     __syncwarp();
   } else {
-    const int r = r0 + warp;
-    const int row = warp * 32 + lane;
+    // warps w and w + 4 share TMEM lane quarter w & 3 (= block-row r0 + (w & 3)); each owns 16 of a slot's 32 columns
+    const int qd = warp & 3, hc = warp >> 2;
+    const int r = r0 + qd;
+    const int row = qd * 32 + lane;
     const int qpos = t * kTile + row;
     const bool row_ok = qpos < p.L;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
     const int64_t stat_idx = ((int64_t)b * p.H + h) * p.L + qpos;
     const float neg_lse2 = row_ok ? -p.lse[stat_idx] * kLog2e : 0.f;
+    constexpr int kMath = kBwdMathWarps * 32;
 
     // does any key of this tile carry a non-zero additive mask?  (no: fast path without the mask term)
     uint32_t any_kpm = 0;
     if (p.kpm) {
-      for (int i = threadIdx.x; i < ns * kBlock; i += 128) {
+      for (int i = threadIdx.x; i < ns * kBlock; i += kMath) {
         const int j = i >> 5;
         if (slot_valid(j)) any_kpm |= (p.kpm[(int64_t)b * p.L + slot_block(j) * kBlock + (i & 31)] != 0.f) ? 1u : 0u;
       }
     }
 
-    // delta = rowsum(dO o O) from the swizzled SMEM tiles
+    // delta = rowsum(dO o O) from the swizzled SMEM tiles (both column halves evaluate it; one writes it)
     mbar_wait(bar_ld, 0);
     float delta = 0.f;
 #pragma unroll
@@ -202,9 +220,10 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         delta = fmaf(fa.y, fo.y, delta);
       }
     }
-    if (row_ok) p.delta[stat_idx] = delta;
+    if (row_ok && hc == 0) p.delta[stat_idx] = delta;
     const float neg_delta_s = -delta * p.scale;
-    const bool has_kpm = bar_red_or(1, 128, any_kpm);       // also: every thread is done reading sO (-> sG)
+    const bool has_kpm = bar_red_or(1, kMath, any_kpm);     // also: every thread is done reading sO (-> sG)
+    stamp(2);
 
     auto slot_live = [&](int j) {
       if (r >= g.nb || !slot_valid(j)) return false;
@@ -217,68 +236,81 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int c = 0; c < npass; ++c) {
       mbar_wait(bar_sdp + c, 0);
       tc_fence_after();
+      stamp(3 + 2 * c);
       bool wrote_g = false;
       for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {
         const int j = order(c * PASS + i);
         const bool is_g = is_global(j);
-        uint32_t dsk[16];
-        if (slot_live(j)) {
-          uint32_t sv[32], dv[32], pk[16];
-          tmem_ld32(trow + S::COL_S + 32 * i, sv);
-          tmem_ld32(trow + S::COL_DP + 32 * i, dv);
-          tmem_wait_ld(sv, dv);
+        const bool live = slot_live(j);
+        uint32_t sv[16], dv[16];
+        if (live) {
+          tmem_ld16(trow + S::COL_S + 32 * i + 16 * hc, sv);
+          tmem_ld16(trow + S::COL_DP + 32 * i + 16 * hc, dv);
+          tmem_wait_ld16(sv, dv);
+        }
+        // dS of slot i overwrites S columns [16 i, 16 i + 16), which hold scores the PARTNER warp reads: both column
+        // halves must have pulled their scores of every slot <= i into registers before either stores
+        named_bar_sync(2 + qd, 64);
+        uint32_t dsk[8];
+        if (live) {
+          uint32_t pk[8];
           const bool diag = g.causal && (slot_block(j) == r);
           float kmine = 0.f;
           if (has_kpm) kmine = p.kpm[(int64_t)b * p.L + slot_block(j) * kBlock + lane] * kLog2e;
 #pragma unroll
-          for (int cc = 0; cc < 32; cc += 2) {
+          for (int cc = 0; cc < 16; cc += 2) {
+            const int col = 16 * hc + cc;
             float x0 = fmaf(__uint_as_float(sv[cc]), p.scale_log2, neg_lse2);
             float x1 = fmaf(__uint_as_float(sv[cc + 1]), p.scale_log2, neg_lse2);
             if (has_kpm) {
-              x0 += __shfl_sync(0xffffffffu, kmine, cc);
-              x1 += __shfl_sync(0xffffffffu, kmine, cc + 1);
+              x0 += __shfl_sync(0xffffffffu, kmine, col);
+              x1 += __shfl_sync(0xffffffffu, kmine, col + 1);
             }
             float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
             if (diag) {
-              if (!((below_diag >> cc) & 1u)) p0 = 0.f;
-              if (!((below_diag >> (cc + 1)) & 1u)) p1 = 0.f;
+              if (!((below_diag >> col) & 1u)) p0 = 0.f;
+              if (!((below_diag >> (col + 1)) & 1u)) p1 = 0.f;
             }
             const float d0 = p0 * fmaf(__uint_as_float(dv[cc]), p.scale, neg_delta_s);
             const float d1 = p1 * fmaf(__uint_as_float(dv[cc + 1]), p.scale, neg_delta_s);
             dsk[cc >> 1] = Elem<T>::pack(d0, d1);
             if (is_g) pk[cc >> 1] = Elem<T>::pack(p0, p1);
           }
-          if (is_g) {
+          if (is_g) {     // row of [P_0 (64 B) | dS_0 (64 B)]: this half owns two 16-byte chunks of each
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, ch)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, 4 + ch)) = make_uint4(dsk[4 * ch], dsk[4 * ch + 1], dsk[4 * ch + 2], dsk[4 * ch + 3]);
+            for (int ch = 0; ch < 2; ++ch) {
+              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, 2 * hc + ch)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, 4 + 2 * hc + ch)) = make_uint4(dsk[4 * ch], dsk[4 * ch + 1], dsk[4 * ch + 2], dsk[4 * ch + 3]);
             }
             wrote_g = true;
           }
         } else {
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) dsk[cc] = 0u;
+          for (int cc = 0; cc < 8; ++cc) dsk[cc] = 0u;
           if (is_g) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) *reinterpret_cast<uint4*>(sG + swz_off<128>(row, ch)) = make_uint4(0, 0, 0, 0);
+            for (int ch = 0; ch < 2; ++ch) {
+              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, 2 * hc + ch)) = make_uint4(0, 0, 0, 0);
+              *reinterpret_cast<uint4*>(sG + swz_off<128>(row, 4 + 2 * hc + ch)) = make_uint4(0, 0, 0, 0);
+            }
             wrote_g = true;
           }
         }
-        tmem_st16(trow + S::COL_S + 16 * i, dsk);
+        tmem_st8(trow + S::COL_S + 16 * i + 8 * hc, dsk);
       }
       if (wrote_g) fence_proxy_async();        // sG is read by the tensor core through the async proxy
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_ds + c);
+      stamp(4 + 2 * c);
     }
 
     mbar_wait(bar_dq, 0);
     tc_fence_after();
-#pragma unroll
-    for (int half = 0; half < DH / 32; ++half) {
+    stamp(9);
+    {   // this half's 32 of the 64 dQ columns -> 16-bit -> swizzled staging tile (the dO tile is free by now)
       uint32_t v[32];
-      tmem_ld32(trow + S::COL_DQ + 32 * half, v);
+      tmem_ld32(trow + S::COL_DQ + 32 * hc, v);
       tmem_wait_ld(v);
 #pragma unroll
       for (int cq = 0; cq < 4; ++cq) {
@@ -287,32 +319,35 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         w.y = Elem<T>::pack(__uint_as_float(v[cq * 8 + 2]), __uint_as_float(v[cq * 8 + 3]));
         w.z = Elem<T>::pack(__uint_as_float(v[cq * 8 + 4]), __uint_as_float(v[cq * 8 + 5]));
         w.w = Elem<T>::pack(__uint_as_float(v[cq * 8 + 6]), __uint_as_float(v[cq * 8 + 7]));
-        *reinterpret_cast<uint4*>(sDO + swz_off<ROWB>(row, half * 4 + cq)) = w;     // the dO tile is free by now
+        *reinterpret_cast<uint4*>(sDO + swz_off<ROWB>(row, hc * 4 + cq)) = w;
       }
     }
     fence_proxy_async();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kMath);
     if (threadIdx.x == 0) {
       tma_store_4d(&tmDQ, sDO, 0, t * kTile, h, b);
       tma_store_commit();
     }
+    stamp(10);
     if (g.cls) {
       // rows 0..63 of G: dV_0^T[d][key] in columns 0..31 ; rows 64..127: dK_0^T[d][key] in columns 32..63
       const int which = row < 64 ? 1 : 0;             // gacc[..., 0] = dK, gacc[..., 1] = dV
       const int d = row & 63;
-      uint32_t v[32];
-      tmem_ld32(trow + S::COL_G + (which ? 0 : 32), v);
-      tmem_wait_ld(v);
+      uint32_t v[16];
+      tmem_ld16(trow + S::COL_G + (which ? 0 : 32) + 16 * hc, v);
+      tmem_wait_ld16(v);
       float* dst = p.gacc + (((int64_t)b * p.H + h) * 2 + which) * (kBlock * DH) + d;
 #pragma unroll
-      for (int cc = 0; cc < 32; ++cc) atomicAdd(dst + cc * DH, __uint_as_float(v[cc]));
+      for (int cc = 0; cc < 16; ++cc) atomicAdd(dst + (16 * hc + cc) * DH, __uint_as_float(v[cc]));
     }
+    stamp(11);
     if (threadIdx.x == 0) tma_store_wait_read();
+    stamp(12);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<256>(tmem_base);
+  if (warp == kBwdMathWarps) tmem_dealloc<256>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------ dK/dV pass
@@ -360,6 +395,12 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   const TileGeom g = p.g;
   const int nq = g.nband;
   const int npass = (nq + PASS - 1) / PASS;
+  long long* tl = nullptr;
+  if (p.timeline && lane == 0 && (warp == 0 || warp == 3 || warp == 4))
+    tl = p.timeline + ((((int64_t)gridDim.z * gridDim.y * gridDim.x) + (((int64_t)b * gridDim.y + h) * gridDim.x + t)) * 3 +
+                       (warp == 0 ? 0 : warp == 3 ? 1 : 2)) * 16;
+  auto stamp = [&](int k) { if (tl) tl[k] = clock64(); };
+  stamp(0);
   const int c0 = 4 * t;
   const int q_lo = c0 - g.nsup;                       // query block of slot 0
   auto slot_valid = [&](int i) { int qb = q_lo + i; return qb >= 0 && qb < g.nb; };
@@ -381,6 +422,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  stamp(1);
 
   if (warp == 4) {
     {   // warp-convergent issue path
@@ -403,14 +445,17 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
                  make_smem_desc(do_addr + c * PASS * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
         }
       };
+      stamp(2);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
+      stamp(3);
       issue_s_dp(0);
       tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_pds + c, 0);
         tc_fence_after();
+        stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < nq; ++i) {
           const int slot = c * PASS + i;
 #pragma unroll
@@ -429,6 +474,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         } else {
           tc_commit_w(bar_out);
         }
+        stamp(5 + 2 * c);
       }
     }
     __syncwarp();
@@ -452,6 +498,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       sNegDelta[i] = dl;
     }
     named_bar_sync(1, 128);
+    stamp(2);
 
     const bool key_global = g.cls && c == 0;           // handled by the dQ pass
     auto slot_live = [&](int i) {
@@ -464,6 +511,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     for (int cpass = 0; cpass < npass; ++cpass) {
       mbar_wait(bar_sdp + cpass, 0);
       tc_fence_after();
+      stamp(3 + 2 * cpass);
       for (int i = 0; i < PASS && cpass * PASS + i < nq; ++i) {
         const int slot = cpass * PASS + i;
         uint32_t pk[16], dsk[16];
@@ -500,10 +548,12 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_pds + cpass);
+      stamp(4 + 2 * cpass);
     }
 
     mbar_wait(bar_out, 0);
     tc_fence_after();
+    stamp(11);
     const float* gk = p.gacc + (((int64_t)b * p.H + h) * 2 + 0) * (kBlock * DH) + lane * DH;
     const float* gv = gk + kBlock * DH;
 #pragma unroll
@@ -538,6 +588,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tma_store_commit();
       tma_store_wait_read();
     }
+    stamp(12);
   }
 
   tc_fence_before();
@@ -574,6 +625,7 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
 
   BwdParams p;
   p.kpm = kpm; p.lse = lse; p.delta = delta; p.gacc = gacc;
+  p.timeline = g_bwd_timeline;
   p.L = L; p.H = H; p.g = g;
   p.scale = d->scale; p.scale_log2 = d->scale * kLog2e;
 
@@ -603,7 +655,7 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
   dim3 grid((L + kTile - 1) / kTile, H, B);
   {
     ScopedKernelTimer timer("attn_bwd_dq_sm100", st);
-    kq<<<grid, kThreads, DqSmem<DH>::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tDQ128, p);
+    kq<<<grid, kBwdThreads, DqSmem<DH>::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tDQ128, p);
   }
   SVAE_CUDA_CHECK(cudaGetLastError());
   {

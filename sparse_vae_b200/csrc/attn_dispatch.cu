@@ -14,6 +14,7 @@ int exact_bwd(const svae_attn_desc*, const void*, const void*, const void*, cons
 
 namespace sm100 {
 
+extern long long* g_bwd_timeline;
 int fwd(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, float*, long long*, cudaStream_t);
 bool fwd_persist_supported(const svae_attn_desc*);
 int fwd_persist(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, long long*, cudaStream_t);
@@ -157,3 +158,5 @@ extern "C" int svae_attn_bwd(const svae_attn_desc* d, const void* q, const void*
   SVAE_REQUIRE(ok, SVAE_ERR_INVALID, "svae_attn_bwd: 16-bit tensors must be 16-byte aligned with strides that are multiples of 8 elements");
   return sm100::bwd(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
 }
+
+extern "C" void svae_debug_set_bwd_timeline(long long* timeline) { svae::sm100::g_bwd_timeline = timeline; }

@@ -87,6 +87,7 @@ struct BwdParams {
   int L, H;
   TileGeom g;
   float scale, scale_log2;
+  long long* timeline;  // debug: [2 kernels][num_ctas][3 roles (warp 0, warp 3, MMA warp)][16] clock64 stamps, or null
 };
 
 // ---- per-slot CUDA-core work on one row's 32 scores held in registers --------------------------------------

@@ -140,6 +140,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+#define SVAE_DEP8(r, o) "+r"(r[o]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+// Ties two 16-register tcgen05.ld results to the wait.
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SVAE_DEP8(a, 0), SVAE_DEP8(a, 8) : : "memory");
+  asm volatile("" : SVAE_DEP8(b, 0), SVAE_DEP8(b, 8) : : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : SVAE_DEP8(a, 0), SVAE_DEP8(a, 8) : : "memory");
+}
+
 // ---- descriptors -----------------------------------------------------------------------------------
 // UMMA shared-memory matrix descriptor (sm_100): start address, LBO, SBO (all >> 4), version 1, swizzle mode.
 //   swizzle_bytes: 128 -> layout_type 2, 64 -> 4, 32 -> 6, 0 -> none.
@@ -161,7 +177,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fmt, int a_m
 }
 
 // Ties the registers of a preceding tcgen05.ld to the wait, so no use of them can be scheduled above it.
-#define SVAE_DEP8(r, o) "+r"(r[o]), "+r"(r[o + 1]), "+r"(r[o + 2]), "+r"(r[o + 3]), "+r"(r[o + 4]), "+r"(r[o + 5]), "+r"(r[o + 6]), "+r"(r[o + 7])
 __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : SVAE_DEP8(r, 0), SVAE_DEP8(r, 8) : : "memory");
   asm volatile("" : SVAE_DEP8(r, 16), SVAE_DEP8(r, 24) : : "memory");
