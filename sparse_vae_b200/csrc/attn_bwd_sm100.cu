@@ -95,17 +95,26 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     return blk >= g.cls && blk < g.nb;
   };
 
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023u) { printf("svae: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_dq, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, kBwdMathWarps * 32); }
-    fence_barrier_init();
-  }
   if (warp == kBwdMathWarps) {
+    // the issuing warp initialises the barriers and starts the TMA loads at once: they overlap the TMEM allocation
+    // and the CTA-wide sync below instead of following them
     if (lane == 0) {
-      prefetch_tensormap(&tmQ); prefetch_tensormap(&tmDO); prefetch_tensormap(&tmO); prefetch_tensormap(&tmK);
-      prefetch_tensormap(&tmV); prefetch_tensormap(&tmKband); prefetch_tensormap(&tmVband); prefetch_tensormap(&tmDQ);
+      if (smem_u32(smem) & 1023u) __trap();     // dynamic shared memory must be 1024-byte aligned (SWIZZLE_128B)
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_dq, 1);
+      for (int i = 0; i < 3; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, kBwdMathWarps * 32); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    mbar_arrive_expect_tx_w(bar_ld, 3 * S::TILE_BYTES + 2 * ns * S::SLOT_BYTES);
+    tma_load_4d_w(sQ, &tmQ, bar_ld, 0, t * kTile, h, b);
+    tma_load_4d_w(sDO, &tmDO, bar_ld, 0, t * kTile, h, b);
+    tma_load_4d_w(sO, &tmO, bar_ld, 0, t * kTile, h, b);
+    tma_load_4d_w(sK, &tmKband, bar_ld, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
+    tma_load_4d_w(sV, &tmVband, bar_ld, 0, band_lo * kBlock, h, b);
+    if (g.cls) {
+      tma_load_4d_w(sK + g.nband * S::SLOT_BYTES, &tmK, bar_ld, 0, 0, h, b);
+      tma_load_4d_w(sV + g.nband * S::SLOT_BYTES, &tmV, bar_ld, 0, 0, h, b);
     }
     tmem_alloc<256>(tmem_slot);
   }
@@ -117,17 +126,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp == kBwdMathWarps) {
     {   // the whole warp runs the issue path convergently; one lane is elected inside each wrapper
-      mbar_arrive_expect_tx_w(bar_ld, 3 * S::TILE_BYTES + 2 * ns * S::SLOT_BYTES);
-      tma_load_4d_w(sQ, &tmQ, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d_w(sDO, &tmDO, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d_w(sO, &tmO, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d_w(sK, &tmKband, bar_ld, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
-      tma_load_4d_w(sV, &tmVband, bar_ld, 0, band_lo * kBlock, h, b);
-      if (g.cls) {
-        tma_load_4d_w(sK + g.nband * S::SLOT_BYTES, &tmK, bar_ld, 0, 0, h, b);
-        tma_load_4d_w(sV + g.nband * S::SLOT_BYTES, &tmV, bar_ld, 0, 0, h, b);
-      }
-
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV),
                      g_addr = smem_u32(sG);
       const uint32_t idesc_dq = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
@@ -405,17 +403,20 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   const int q_lo = c0 - g.nsup;                       // query block of slot 0
   auto slot_valid = [&](int i) { int qb = q_lo + i; return qb >= 0 && qb < g.nb; };
 
-  if (threadIdx.x == 0) {
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_out, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_pds + i, 128); }
-    fence_barrier_init();
-  }
   if (warp == 4) {
+    // barriers + TMA loads first: they overlap the TMEM allocation and the CTA-wide sync
     if (lane == 0) {
-      prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmQband);
-      prefetch_tensormap(&tmDOband); prefetch_tensormap(&tmDK); prefetch_tensormap(&tmDV);
+      mbar_init(bar_ld, 1);
+      mbar_init(bar_out, 1);
+      for (int i = 0; i < 4; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_pds + i, 128); }
+      fence_barrier_init();
     }
+    __syncwarp();
+    mbar_arrive_expect_tx_w(bar_ld, 2 * S::TILE_BYTES + 2 * nq * S::SLOT_BYTES);
+    tma_load_4d_w(sK, &tmK, bar_ld, 0, t * kTile, h, b);
+    tma_load_4d_w(sV, &tmV, bar_ld, 0, t * kTile, h, b);
+    tma_load_4d_w(sQ, &tmQband, bar_ld, 0, q_lo * kBlock, h, b);      // rows outside [0, L) -> zeros
+    tma_load_4d_w(sDO, &tmDOband, bar_ld, 0, q_lo * kBlock, h, b);
     tmem_alloc<256>(tmem_slot);
   }
   tc_fence_before();
@@ -426,12 +427,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 
   if (warp == 4) {
     {   // warp-convergent issue path
-      mbar_arrive_expect_tx_w(bar_ld, 2 * S::TILE_BYTES + 2 * nq * S::SLOT_BYTES);
-      tma_load_4d_w(sK, &tmK, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d_w(sV, &tmV, bar_ld, 0, t * kTile, h, b);
-      tma_load_4d_w(sQ, &tmQband, bar_ld, 0, q_lo * kBlock, h, b);      // rows outside [0, L) -> zeros
-      tma_load_4d_w(sDO, &tmDOband, bar_ld, 0, q_lo * kBlock, h, b);
-
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sDO);
       const uint32_t idesc_o = make_idesc(kTile, DH, Elem<T>::fmt, 0, 1);
       auto issue_s_dp = [&](int c) {   // S^T = K Q^T, dP^T = V dO^T for the chunk's (<= 2) query slots
