@@ -102,3 +102,59 @@ def test_grad_checkpointing_recompute_is_deterministic():
         norms.append(model.decoder_layers[0].attention.q_linear.weight.grad.float().norm().item())
     assert losses[0] == losses[1]
     assert abs(norms[0] - norms[1]) <= 1e-3 * norms[0]
+
+
+def test_fused_head_matches_unfused_logits_path():
+    """`training_step` (fused vocabulary head + cross-entropy) against `reconstruct` -> `get_nll` (materialised logits,
+    the reference's literal path) on the same model, same z: identical objective."""
+    case = mg.MODEL_CASE
+    dev = torch.device('cuda')
+    sv, model = _build(case, dev)
+    batch = _batch(sv, case, dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from sparse_vae_b200.core.padded_tensor import split_padding
+    tokens, padding = split_padding(batch['token_ids'])
+    original = tokens.long()
+    padding = original.eq(0) if padding is None else padding
+    with torch.no_grad():
+        x = model.input_layer(original)
+        z = torch.randn(original.shape[0], 1, case['latent'], device=dev)
+        logits = model.reconstruct(x, z, padding=padding)[..., :-1, :]
+        nll_ref = model.get_nll(logits, original[..., 1:])
+        hidden = model.reconstruct(x, z, padding=padding, return_hidden=True)
+        from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+        nll = fused_vocab_nll(hidden, model.output_layer[-1], original[..., 1:])
+    assert abs(nll.item() - nll_ref.item()) <= 1e-5 * abs(nll_ref.item())
+
+
+def test_long_context_training_step_runs():
+    """BASELINE config 4 shape per GPU: batch 4 x 16384 tokens, bf16; more than 2**30 logits -> two CE chunks."""
+    import sparse_vae_b200 as sv
+    from sparse_vae_b200.core.lightning_shim import to_attrdict
+    from sparse_vae_b200.synthetic import synthetic_tokens, to_device
+    dev = torch.device('cuda')
+    torch.manual_seed(0)
+    model = sv.TransformerVAE(to_attrdict(sv.TransformerVAEHparams())).to(dev)
+    model.initialize_weights()
+    batch = to_device(synthetic_tokens(4, 16384, seed=3), dev)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        loss = model.training_step(batch, 0)['loss']
+    loss.backward()
+    assert torch.isfinite(loss) and 9.5 < loss.item() < 11.5          # ~ln(32768) at random init
+    gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in model.parameters() if p.grad is not None))
+    assert torch.isfinite(gn) and gn.item() > 0
+
+
+def test_autoregressive_sample_and_eval_paths_run():
+    """`sample()` (KV-cache decoding, dense branch -- SURVEY 3.3) and `validation_step` on the GPU."""
+    case = mg.MODEL_CASE
+    dev = torch.device('cuda')
+    sv, model = _build(case, dev)
+    model.hparams.kl_weight = 1.0
+    model.start_token, model.end_token = 1, 2
+    with torch.no_grad():
+        ids = model.sample(max_length=48, batch_size=3)
+    assert ids.shape[0] == 3 and 1 <= ids.shape[1] <= 48 and ((ids >= 0) & (ids < 2 ** 15)).all()
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        model.validation_step(_batch(sv, case, dev), 0)
+    assert torch.isfinite(model.logged['val_nll']) and torch.isfinite(model.logged['val_loss'])
