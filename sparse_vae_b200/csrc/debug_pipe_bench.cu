@@ -10,7 +10,7 @@ namespace sm100 {
 
 using namespace ptx;
 
-__global__ void __launch_bounds__(512, 1) pipe_bench_kernel(int mode, int iters, long long* out, float seed) {
+__global__ void __launch_bounds__(256, 1) pipe_bench_kernel(int mode, int iters, long long* out, float seed) {
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
@@ -100,6 +100,50 @@ __global__ void __launch_bounds__(512, 1) pipe_bench_kernel(int mode, int iters,
     }
     a[0] += l0 + l1;
   }
+  else if (mode == 8 || mode == 9) {
+    // the forward kernel's softmax of one block-row: 5 live slots (160 scores) in registers.
+    // mode 8: pass 2 only (exp2 + pack + tcgen05.st); mode 9: pass 1 (5 x tcgen05.ld + max) + pass 2
+    uint32_t s0[32], s1[32], s2[32], s3[32], s4[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      s0[i] = __float_as_uint(seed * (float)(i + lane)); s1[i] = __float_as_uint(seed * (float)(i + 2 * lane));
+      s2[i] = __float_as_uint(seed * (float)(2 * i + lane)); s3[i] = __float_as_uint(seed * (float)(3 * i + lane));
+      s4[i] = __float_as_uint(seed * (float)(i + 3 * lane));
+    }
+    const float scale_log2 = 0.18f;
+    float l0 = 0.f, l1 = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      float m = -INFINITY;
+      if (mode == 9) {
+        tmem_ld32(trow, s0); tmem_ld32(trow + 32, s1); tmem_ld32(trow + 64, s2); tmem_ld32(trow + 96, s3); tmem_ld32(trow + 128, s4);
+        tmem_wait_ld();
+        tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3); tmem_dep(s4);
+        mask_above_diag(s4, (2u << lane) - 1u);
+        m = slot_max(s0, m, false, nullptr, scale_log2);
+        m = slot_max(s1, m, false, nullptr, scale_log2);
+        m = slot_max(s2, m, false, nullptr, scale_log2);
+        m = slot_max(s3, m, false, nullptr, scale_log2);
+        m = slot_max(s4, m, false, nullptr, scale_log2);
+        m *= scale_log2;
+      } else {
+        m = 3.0f + (float)(it & 3);
+      }
+      const float neg_m = (m == -INFINITY) ? 0.f : -m;
+      uint32_t pk[16];
+      slot_exp_pack<__nv_bfloat16>(s0, pk, l0, l1, false, nullptr, scale_log2, neg_m); tmem_st16(trow + 256, pk);
+      slot_exp_pack<__nv_bfloat16>(s1, pk, l0, l1, false, nullptr, scale_log2, neg_m); tmem_st16(trow + 256 + 16, pk);
+      slot_exp_pack<__nv_bfloat16>(s2, pk, l0, l1, false, nullptr, scale_log2, neg_m); tmem_st16(trow + 256 + 32, pk);
+      slot_exp_pack<__nv_bfloat16>(s3, pk, l0, l1, false, nullptr, scale_log2, neg_m); tmem_st16(trow + 256 + 48, pk);
+      slot_exp_pack<__nv_bfloat16>(s4, pk, l0, l1, false, nullptr, scale_log2, neg_m); tmem_st16(trow + 256 + 64, pk);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pk[c] = 0u;
+      tmem_st16(trow + 256 + 80, pk); tmem_st16(trow + 256 + 96, pk); tmem_st16(trow + 256 + 112, pk);
+      tmem_wait_st();
+      if (mode == 8) { s0[it & 31] ^= 1u; }      // keep iterations distinct
+    }
+    a[0] += l0 + l1;
+    acc ^= s0[3] ^ s4[7];
+  }
   const long long t1 = clock64();
   float sum = 0.f;
 #pragma unroll
@@ -117,7 +161,7 @@ __global__ void __launch_bounds__(512, 1) pipe_bench_kernel(int mode, int iters,
 extern "C" __attribute__((visibility("default"))) int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out,
                                                                             void* stream) {
   using namespace svae;
-  SVAE_REQUIRE(warps >= 1 && warps <= 16 && mode >= 0 && mode <= 7, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
+  SVAE_REQUIRE(warps >= 1 && warps <= 8 && mode >= 0 && mode <= 9, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
   sm100::pipe_bench_kernel<<<1, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, out, 0.25f);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;

@@ -9,16 +9,16 @@ from sparse_vae_b200 import _native as N  # noqa: E402
 
 out = torch.zeros(64, dtype=torch.int64, device='cuda')
 iters = 256
-names = ['MUFU.EX2', 'F2FP bf16x2 pack', 'FFMA', 'FMNMX3', 'tcgen05.ld x32 (4 KB)', 'tcgen05.st x16 (2 KB)', 'softmax step (4 elem)', 'softmax step, 96 elem unrolled']
-print(f'cycles per warp instruction (modes 6, 7: per PAIR of elements), {iters} x 8 instructions per warp')
+names = ['MUFU.EX2', 'F2FP bf16x2 pack', 'FFMA', 'FMNMX3', 'tcgen05.ld x32 (4 KB)', 'tcgen05.st x16 (2 KB)', 'softmax step (4 elem)', 'softmax step, 96 elem unrolled', 'fwd softmax pass 2 (160 scores in regs)', 'fwd softmax pass 1 + 2 (5 LDTM + max + exp)']
+print(f'cycles per warp instruction (modes 6, 7: per PAIR of elements; modes 8, 9: cycles per block-row softmax), {iters} x 8 instructions per warp')
 for mode, name in enumerate(names):
     row = []
-    for warps in (1, 4, 8, 16):
+    for warps in (1, 4, 8):
         for _ in range(2):
             out.zero_()
             N.check(N.lib.svae_debug_pipe_bench(mode, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
             torch.cuda.synchronize()
-        cyc = out[:warps].max().item() / (iters * {6: 4, 7: 48}.get(mode, 8))
+        cyc = out[:warps].max().item() / (iters * {6: 4, 7: 48, 8: 1, 9: 1}.get(mode, 8))
         row.append(f'{warps:2d} warps {cyc:7.2f}')
     print(f'  {name:24s} ' + ' | '.join(row))
 print('(4 warps = one per SMSP; 8 / 16 warps = 2 / 4 per SMSP sharing that SMSP\'s pipes and TMEM lane quarter)')
