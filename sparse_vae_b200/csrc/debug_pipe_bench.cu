@@ -10,14 +10,45 @@ namespace sm100 {
 
 using namespace ptx;
 
-__global__ void __launch_bounds__(256, 1) pipe_bench_kernel(int mode, int iters, long long* out, float seed) {
+__global__ void __launch_bounds__(256, 1) pipe_bench_kernel(int mode_in, int iters, long long* out, float seed) {
   __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t mma_bar;
+  __shared__ volatile int stop_flag;
+  extern __shared__ __align__(1024) uint8_t dsmem[];
+  const int mode = mode_in & 0xff;
+  const bool with_mma = (mode_in & 0x100) != 0;      // the LAST warp issues back-to-back S-like MMAs (M=128, N=256) meanwhile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (with_mma) {
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dsmem)[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(&mma_bar, 1); fence_barrier_init(); stop_flag = 0; }
+    fence_proxy_async();
+  }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t trow = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  const int nwarps = blockDim.x >> 5;
+  if (with_mma && warp == nwarps - 1) {
+    // interference generator: S = Q K^T shaped MMAs into TMEM columns 0..255 (the columns the other warps read)
+    const uint32_t a_addr = smem_u32(dsmem), b_addr = smem_u32(dsmem + 16 * 1024);
+    const uint32_t idesc = make_idesc(128, 256, 1, 0, 0);
+    long long n = 0;
+    __syncthreads();                                   // matches the barrier in front of the timed region below
+    while (!stop_flag && n < (1 << 22)) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_ss_w(tmem_slot, make_smem_desc(a_addr + ks * 32, 16, 1024, 128), make_smem_desc(b_addr + ks * 32, 16, 1024, 128), idesc, 1u);
+      tc_commit_w(&mma_bar);
+      mbar_wait(&mma_bar, (uint32_t)(n & 1));
+      ++n;
+    }
+    if (lane == 0) out[62] = n;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_slot);
+    return;
+  }
   float a[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = seed + 0.01f * (float)(i + lane);
@@ -149,6 +180,11 @@ __global__ void __launch_bounds__(256, 1) pipe_bench_kernel(int mode, int iters,
 #pragma unroll
   for (int i = 0; i < 8; ++i) sum += a[i];
   if (lane == 0) out[warp] = t1 - t0;
+  if (with_mma) {
+    __threadfence_block();
+    named_bar_sync(1, (nwarps - 1) * 32);
+    if (threadIdx.x == 0) stop_flag = 1;
+  }
   if (sum == 1234.5678f || acc == 0x12345u || v[3] == 0xdeadbeefu) out[63] = 1;     // keep the work alive
   tc_fence_before();
   __syncthreads();
@@ -161,8 +197,10 @@ __global__ void __launch_bounds__(256, 1) pipe_bench_kernel(int mode, int iters,
 extern "C" __attribute__((visibility("default"))) int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out,
                                                                             void* stream) {
   using namespace svae;
-  SVAE_REQUIRE(warps >= 1 && warps <= 8 && mode >= 0 && mode <= 9, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
-  sm100::pipe_bench_kernel<<<1, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(mode, iters, out, 0.25f);
+  SVAE_REQUIRE(warps >= 1 && warps <= 8 && (mode & 0xff) >= 0 && (mode & 0xff) <= 9, SVAE_ERR_INVALID, "svae_debug_pipe_bench: bad arguments");
+  auto kern = sm100::pipe_bench_kernel;
+  SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024 + 1024));
+  kern<<<1, warps * 32, 48 * 1024 + 1024, static_cast<cudaStream_t>(stream)>>>(mode, iters, out, 0.25f);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }

@@ -22,3 +22,15 @@ for mode, name in enumerate(names):
         row.append(f'{warps:2d} warps {cyc:7.2f}')
     print(f'  {name:24s} ' + ' | '.join(row))
 print('(4 warps = one per SMSP; 8 / 16 warps = 2 / 4 per SMSP sharing that SMSP\'s pipes and TMEM lane quarter)')
+
+print('with a 5th / 9th warp issuing back-to-back S-shaped tcgen05.mma (M=128, N=256, K=64) into the TMEM columns being read:')
+for mode, name in ((4, 'tcgen05.ld x32 (4 KB)'), (5, 'tcgen05.st x16 (2 KB)'), (8, 'fwd softmax pass 2'), (9, 'fwd softmax pass 1 + 2')):
+    row = []
+    for warps in (5,):
+        for _ in range(2):
+            out.zero_()
+            N.check(N.lib.svae_debug_pipe_bench(mode | 0x100, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
+            torch.cuda.synchronize()
+        cyc = out[:warps - 1].max().item() / (iters * {6: 4, 7: 48, 8: 1, 9: 1}.get(mode, 8))
+        row.append(f'{warps - 1} warps + MMA {cyc:8.2f}  (MMA groups issued meanwhile: {out[62].item()})')
+    print(f'  {name:24s} ' + ' | '.join(row))
