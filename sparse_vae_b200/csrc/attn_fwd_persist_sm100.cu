@@ -298,52 +298,45 @@ attn_fwd_persist_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
       mbar_wait(s_ready + grp, n & 1);
       tc_fence_after();
       if (tl) tl[1] = clock64();
-      // ---- pass 1: row maximum.  The band scores stay in registers for pass 2; the global block is re-read.
-      uint32_t s0[32], s1[32], s2[32], s3[32];
+      // Both passes are ROLLED loops over the block-row's live slots (k = 0: global block, k = 1..4: band slot
+      // first + k - 1), re-reading the scores from TMEM in pass 2: tcgen05.ld is cheap (~53 cycles per 4 KB per SMSP,
+      // tests/pipe_bench.py) while ~1.5 k instructions of straight-line code per tile do not fit the instruction
+      // cache next to the other warps' streams (13 % `no_inst` stalls in profiles/r01b_persist_hot_sass.txt).
       float m = -INFINITY, l0 = 0.f, l1 = 0.f;
       const bool g_diag = g.causal && g.cls && r == 0 && lg;      // block-row 0: the global block IS the diagonal
-      if (lv[0]) tmem_ld32(trow + 32 * (first + 0), s0);
-      if (lv[1]) tmem_ld32(trow + 32 * (first + 1), s1);
-      if (lv[2]) tmem_ld32(trow + 32 * (first + 2), s2);
-      if (lv[3]) tmem_ld32(trow + 32 * (first + 3), s3);
-      if (lg) {
-        uint32_t sg[32];
-        tmem_ld32(trow, sg);
-        tmem_wait_ld(sg);                          // waits for every load above as well
-        if (g_diag) mask_above_diag(sg, below_diag);
-        m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
-      } else {
-        tmem_wait_ld();
+      uint32_t live_bits = lg ? 1u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) live_bits |= lv[kk] ? (2u << kk) : 0u;
+      // ---- pass 1: row maximum
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) {
+        if (!((live_bits >> k) & 1u)) continue;
+        const int j = k == 0 ? 0 : first + k - 1;
+        uint32_t v[32];
+        tmem_ld32(trow + 32 * j, v);
+        tmem_wait_ld(v);
+        if (k == 0 ? g_diag : (kdiag == k - 1)) mask_above_diag(v, below_diag);
+        m = slot_max(v, m, has_kpm, sKpm + j * kBlock, p.scale_log2);
       }
-      tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
-      if (kdiag == 0 && lv[0]) mask_above_diag(s0, below_diag);
-      if (kdiag == 1 && lv[1]) mask_above_diag(s1, below_diag);
-      if (kdiag == 2 && lv[2]) mask_above_diag(s2, below_diag);
-      if (kdiag == 3 && lv[3]) mask_above_diag(s3, below_diag);
-
-      if (lv[0]) m = slot_max(s0, m, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2);
-      if (lv[1]) m = slot_max(s1, m, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2);
-      if (lv[2]) m = slot_max(s2, m, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2);
-      if (lv[3]) m = slot_max(s3, m, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2);
       if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
       const float neg_m = (m == -INFINITY) ? 0.f : -m;
       if (tl) tl[2] = clock64();
 
-      // ---- pass 2: P = exp2(s * scale_log2 + mask - m), written over S as packed 16-bit
+      // ---- pass 2: P = exp2(s * scale_log2 + mask - m), written over S as packed 16-bit.  Slots are visited in
+      //      increasing column order, so P_j (columns 16 j ..) only ever overwrites scores that were already consumed.
       if (p.stagger_cycles >= 0) named_bar_sync(4 + grp, 256);
       uint32_t pk[16];
-      if (lg) {
-        uint32_t sg[32];                         // re-read (keeps 32 registers free across the two passes)
-        tmem_ld32(trow, sg);
-        tmem_wait_ld(sg);
-        if (g_diag) mask_above_diag(sg, below_diag);
-        slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m);
-        tmem_st16(trow, pk);
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) {
+        if (!((live_bits >> k) & 1u)) continue;
+        const int j = k == 0 ? 0 : first + k - 1;
+        uint32_t v[32];
+        tmem_ld32(trow + 32 * j, v);
+        tmem_wait_ld(v);
+        if (k == 0 ? g_diag : (kdiag == k - 1)) mask_above_diag(v, below_diag);
+        slot_exp_pack<T>(v, pk, l0, l1, has_kpm, sKpm + j * kBlock, p.scale_log2, neg_m);
+        tmem_st16(trow + 16 * j, pk);
       }
-      if (lv[0]) { slot_exp_pack<T>(s0, pk, l0, l1, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 0), pk); }
-      if (lv[1]) { slot_exp_pack<T>(s1, pk, l0, l1, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 1), pk); }
-      if (lv[2]) { slot_exp_pack<T>(s2, pk, l0, l1, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 2), pk); }
-      if (lv[3]) { slot_exp_pack<T>(s3, pk, l0, l1, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 3), pk); }
       if (p.stagger_cycles >= 0) named_bar_arrive(4 + (grp ^ 1), 256);
 #pragma unroll
       for (int c = 0; c < 16; ++c) pk[c] = 0u;
