@@ -246,9 +246,11 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           tmem_ld16(trow + S::COL_DP + 32 * i + 16 * hc, dv);
           tmem_wait_ld16(sv, dv);
         }
+        if (c == 0 && i == 0) stamp(13);
         // dS of slot i overwrites S columns [16 i, 16 i + 16), which hold scores the PARTNER warp reads: both column
         // halves must have pulled their scores of every slot <= i into registers before either stores
         named_bar_sync(2 + qd, 64);
+        if (c == 0 && i == 0) stamp(14);
         uint32_t dsk[8];
         if (live) {
           uint32_t pk[8];
@@ -295,6 +297,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
         }
         tmem_st8(trow + S::COL_S + 16 * i + 8 * hc, dsk);
+        if (c == 0 && i == 0) stamp(15);
       }
       if (wrote_g) fence_proxy_async();        // sG is read by the tensor core through the async proxy
       tmem_wait_st();

@@ -50,3 +50,11 @@ print('=== dQ pass, MMA warp'); show(0, 2, i_dq)
 print('=== dK/dV pass, math warp 0'); show(1, 0, m_kv)
 print('=== dK/dV pass, math warp 3'); show(1, 1, m_kv)
 print('=== dK/dV pass, MMA warp'); show(1, 2, i_kv)
+
+x = t[0, :, 0, :]
+ok = x[:, 13] > 0
+print('=== dQ pass, math warp 0, FIRST slot of chunk 0 (live for every tile but the first of a sequence):')
+for a, b2, name in ((3, 13, 'sdp0 ready -> scores in registers (2 x tcgen05.ld.x16 + wait)'), (13, 14, 'pair barrier'),
+                   (14, 15, '16 elements of exp / dS math + tcgen05.st issue')):
+    d = (x[ok, b2] - x[ok, a])
+    print(f'   {name:<70s} mean {d.mean():8.0f}  p10 {np.percentile(d, 10):8.0f}  p90 {np.percentile(d, 90):8.0f}')
