@@ -223,54 +223,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 
     float m = -INFINITY, l0 = 0.f, l1 = 0.f, neg_m;
-    if (kTwoChains) {
-      // ---- this block-row's live slots: the global slot and band slots first .. first + nlb - 1 (nlb <= 4);
-      //      one batch of TMEM loads, scores stay in registers for both passes
-      const int nlb = g.left + g.nsup;
-      const int first = g.cls + warp;
-      const int kdiag = g.causal ? g.left - 1 : -1;              // position of the diagonal block inside the live band
-      const bool lg = g.cls && r < g.nb;
-      bool lv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) lv[k] = k < nlb && r < g.nb && slot_valid(first + k);
-      uint32_t sg[32], s0[32], s1[32], s2[32], s3[32];
-      if (lg) tmem_ld32(trow, sg);
-      if (lv[0]) tmem_ld32(trow + 32 * (first + 0), s0);
-      if (lv[1]) tmem_ld32(trow + 32 * (first + 1), s1);
-      if (lv[2]) tmem_ld32(trow + 32 * (first + 2), s2);
-      if (lv[3]) tmem_ld32(trow + 32 * (first + 3), s3);
-      tmem_wait_ld();
-      tmem_dep(sg); tmem_dep(s0); tmem_dep(s1); tmem_dep(s2); tmem_dep(s3);
-      if (kdiag == 0 && lv[0]) mask_above_diag(s0, below_diag);
-      if (kdiag == 1 && lv[1]) mask_above_diag(s1, below_diag);
-      if (kdiag == 2 && lv[2]) mask_above_diag(s2, below_diag);
-      if (kdiag == 3 && lv[3]) mask_above_diag(s3, below_diag);
-      if (g.causal && g.cls && r == 0 && lg) mask_above_diag(sg, below_diag);   // block-row 0: the global block IS the diagonal
-
-      if (lg) m = slot_max(sg, m, has_kpm, sKpm, p.scale_log2);
-      if (lv[0]) m = slot_max(s0, m, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2);
-      if (lv[1]) m = slot_max(s1, m, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2);
-      if (lv[2]) m = slot_max(s2, m, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2);
-      if (lv[3]) m = slot_max(s3, m, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2);
-      if (!has_kpm) m *= p.scale_log2;        // scale > 0: max commutes with the scaling
-      neg_m = (m == -INFINITY) ? 0.f : -m;
-      stamp(3);
-
-      uint32_t pk[16];
-      if (lg) { slot_exp_pack<T>(sg, pk, l0, l1, has_kpm, sKpm, p.scale_log2, neg_m); tmem_st16(trow, pk); }
-      if (lv[0]) { slot_exp_pack<T>(s0, pk, l0, l1, has_kpm, sKpm + (first + 0) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 0), pk); }
-      if (lv[1]) { slot_exp_pack<T>(s1, pk, l0, l1, has_kpm, sKpm + (first + 1) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 1), pk); }
-      if (lv[2]) { slot_exp_pack<T>(s2, pk, l0, l1, has_kpm, sKpm + (first + 2) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 2), pk); }
-      if (lv[3]) { slot_exp_pack<T>(s3, pk, l0, l1, has_kpm, sKpm + (first + 3) * kBlock, p.scale_log2, neg_m); tmem_st16(trow + 16 * (first + 3), pk); }
-#pragma unroll
-      for (int c = 0; c < 16; ++c) pk[c] = 0u;
-      uint32_t live_mask = lg ? 1u : 0u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) live_mask |= lv[k] ? (1u << (first + k)) : 0u;
-      for (int j = 0; j < ns; ++j)              // P = 0 for the slots this block-row does not attend
-        if (!((live_mask >> j) & 1u)) tmem_st16(trow + 16 * j, pk);
-    } else {
-      // ---- wide windows (9..14 slots): two passes over the live slots, one TMEM round trip per slot
+    {
+      // ---- two ROLLED passes over the block-row's live slots, one TMEM round trip per slot and pass: tcgen05.ld is
+      //      cheap (~53 cycles per 4 KB per SMSP) while straight-line code for 5 x 32 register-resident scores does not
+      //      fit the instruction cache (measured on the persistent kernel: 92 -> 69 us, profiles/README.md)
       for (int j = 0; j < ns; ++j) {
         if (!slot_live(j)) continue;
         uint32_t v[32];
