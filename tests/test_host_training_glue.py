@@ -1,0 +1,111 @@
+"""CPU: host-side logic of the SURVEY 8f rows -- the per-token weights that reproduce `robust_cross_entropy`'s chunked
+mean (reference core/language_model.py:161-170), the RAdam rule on CPU tensors (reference core/rectified_adam.py:15-88),
+the drop-in modules' CPU behaviour, and the autograd glue of the in-place latent-row replacement."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def _reference_robust_ce(logits, labels, chunk_elems):
+    """The reference function with its 2**30 constant made a parameter so that small tensors exercise the chunking."""
+    chunks = -(-logits.numel() // chunk_elems)
+    if chunks == 1:
+        return F.cross_entropy(logits.flatten(end_dim=1), labels.flatten(), ignore_index=0)
+    return torch.stack([F.cross_entropy(lo.flatten(end_dim=1), la.flatten(), ignore_index=0)
+                        for lo, la in zip(logits.chunk(chunks, dim=-2), labels.chunk(chunks, dim=-1))]).mean()
+
+
+@pytest.mark.parametrize('B,S,V,chunk_elems', [(3, 17, 11, 2 ** 30), (3, 17, 11, 200), (2, 64, 8, 300), (4, 33, 5, 100),
+                                               (1, 9, 7, 20)])
+def test_token_weights_reproduce_chunked_mean(monkeypatch, B, S, V, chunk_elems):
+    from sparse_vae_b200.core import fused_ce
+    g = torch.Generator().manual_seed(B * S + V)
+    logits = torch.randn(B, S, V, generator=g, dtype=torch.float64)
+    labels = torch.randint(1, V, (B, S), generator=g)
+    labels[0, S // 2:] = 0
+    labels[-1, -1] = 0
+    ref = _reference_robust_ce(logits, labels, chunk_elems)
+    # _token_weights hard-codes 2**30 like the reference; scale the vocabulary argument so the same chunk count results
+    chunks = -(-(B * S * V) // chunk_elems)
+    fake_vocab = 1 if chunks == 1 else -(-((chunks - 1) * 2 ** 30 + 1) // (B * S))
+    assert -(-(B * S * fake_vocab) // 2 ** 30) == chunks
+    w = fused_ce._token_weights(labels, fake_vocab)
+    nll = F.cross_entropy(logits.flatten(end_dim=1), labels.flatten(), ignore_index=0, reduction='none').view(B, S)
+    got = (nll * w).sum()
+    assert abs(got.item() - ref.item()) <= 1e-6 * abs(ref.item())       # weights are fp32 (they scale an fp32 gradient)
+    assert (w[labels == 0] == 0).all()
+
+
+def test_radam_cpu_path_matches_reference_rule():
+    from sparse_vae_b200.core.rectified_adam import RAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(5, 7), (11,), (2, 3, 4)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g, dtype=torch.float64)) for s in shapes]
+    ref_p = [p.detach().clone() for p in params]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    opt = RAdam(params, lr=1e-2, weight_decay=0.01)
+    beta1, beta2, eps, wd = 0.9, 0.999, 1e-6, 0.01
+    for step in range(1, 9):
+        grads = [torch.randn(s, generator=g, dtype=torch.float64) for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.clone()
+        opt.step()
+        lr = 1e-2
+        beta2_t = beta2 ** step
+        bias_v = (1 - beta2_t) ** 0.5
+        rho_inf = 2.0 / (1.0 - beta2) - 1.0
+        rho_t = rho_inf - 2 * step * beta2_t / (1 - beta2_t)
+        if rho_t > 4:
+            lr *= (((rho_t - 4.0) * (rho_t - 2.0) * rho_inf) / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t)) ** 0.5 * bias_v
+        for p, gr, m, v in zip(ref_p, grads, ref_m, ref_v):
+            m.mul_(beta1).add_(gr, alpha=1 - beta1)
+            v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+            p.mul_(1 - lr * wd)
+            if rho_t > 4:
+                p.addcdiv_(m, (v.sqrt() / bias_v).add_(eps), value=-lr / (1 - beta1 ** step))
+            else:
+                p.add_(m, alpha=-lr / (1 - beta1 ** step))
+    for p, r in zip(params, ref_p):
+        torch.testing.assert_close(p.detach(), r, rtol=1e-12, atol=1e-14)
+
+
+def test_drop_in_modules_on_cpu_are_the_torch_modules():
+    from sparse_vae_b200.core.layer_norm import LayerNorm
+    from sparse_vae_b200.core.linear import Linear
+    ln, lin = LayerNorm(128), Linear(128, 64)
+    assert set(ln.state_dict()) == {'weight', 'bias'} and set(lin.state_dict()) == {'weight', 'bias'}
+    assert isinstance(ln, torch.nn.LayerNorm) and isinstance(lin, torch.nn.Linear)
+    x = torch.randn(3, 5, 128)
+    torch.testing.assert_close(ln(x), F.layer_norm(x, (128,), ln.weight, ln.bias, ln.eps))
+    torch.testing.assert_close(lin(x), F.linear(x, lin.weight, lin.bias))
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        assert lin(x).dtype == torch.bfloat16           # plain nn.Linear behaviour under CPU autocast
+
+
+def test_fused_paths_refuse_cpu_tensors():
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll, supported
+    lin = torch.nn.Linear(8, 8192)
+    assert not supported(torch.randn(1, 4, 8), lin)
+    with pytest.raises(ValueError):
+        fused_vocab_nll(torch.randn(1, 4, 8), lin, torch.ones(1, 3, dtype=torch.long))
+    from sparse_vae_b200.fused_optim import FusedRAdamStep
+    with pytest.raises(ValueError):
+        FusedRAdamStep()([torch.zeros(4)], [torch.zeros(4)], [torch.zeros(4)], [torch.zeros(4)], 1e-3, 0.9, 0.999, 1e-6, 0.0, 1)
+
+
+def test_replace_first_position_matches_cat_and_gradients():
+    from sparse_vae_b200.transformer_vae import _ReplaceFirstPosition
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(2, 6, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    row = torch.randn(2, 1, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    base2, row2 = base.detach().clone().requires_grad_(True), row.detach().clone().requires_grad_(True)
+    w = torch.randn(2, 6, 4, generator=g, dtype=torch.float64)
+    ref = torch.cat([row2, (base2 * 2)[..., 1:, :]], dim=-2)
+    out = _ReplaceFirstPosition.apply(base * 2, row)             # `base * 2` is a temporary, like a layer's output
+    assert torch.equal(out, ref)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert torch.equal(base.grad, base2.grad) and torch.equal(row.grad, row2.grad)
