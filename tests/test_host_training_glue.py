@@ -38,7 +38,8 @@ def test_token_weights_reproduce_chunked_mean(monkeypatch, B, S, V, chunk_elems)
         assert torch.isnan(got)
     else:
         assert abs(got.item() - ref.item()) <= 1e-6 * abs(ref.item())   # weights are fp32 (they scale an fp32 gradient)
-    assert (w[labels == 0] == 0).all()
+    if not torch.isnan(ref):
+        assert (w[labels == 0] == 0).all()
 
 
 def test_radam_cpu_path_matches_reference_rule():
