@@ -55,6 +55,12 @@ class TransformerVAEHparams(TransformerHparams, ContinuousVAEHparams):
 
 
 class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
+    # `validate_args` of the posterior `Normal` returned by `training_step`.  None = torch's default, i.e. the reference's
+    # behaviour: the constructor checks loc / scale on the HOST (`constraint.check(...).all()`), which synchronises the
+    # device in the middle of every step and empties the launch queue.  A trainer that wants the CPU to run ahead of the
+    # GPU sets this to False (bench.py does and says so in its `config`).
+    validate_posterior: Optional[bool] = None
+
     def __init__(self, hparams: DictConfig):
         super().__init__(hparams)
         hp = self.hparams
@@ -90,7 +96,8 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
             self.log(stage + '_mc_mutual_info', kl - marginal_kl(posterior))
 
         if stage == 'train':
-            return {'loss': loss, 'posterior': Normal(loc=posterior.loc.detach(), scale=posterior.scale.detach())}
+            return {'loss': loss, 'posterior': Normal(loc=posterior.loc.detach(), scale=posterior.scale.detach(),
+                                                     validate_args=self.validate_posterior)}
         elif stage == 'val':
             self.log('val_loss', nll + kl)
 
