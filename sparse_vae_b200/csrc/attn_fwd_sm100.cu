@@ -6,9 +6,11 @@
 // One CTA = one 128-query tile (4 block-rows of the 32x32 layout) of one (batch, head).  The union of key blocks
 // those 4 block-rows attend is a contiguous band of (left+3+nsup) blocks plus the global block 0, i.e. <= 8 "slots"
 // of 32 keys at window 4; all of it fits TMEM at once (128 lanes x 32*slots fp32 columns).  Each of the 4 softmax
-// warps owns exactly one block-row (TMEM lane quarter), so block sparsity is warp-uniform: a warp pulls only its
-// LIVE slots (<= 4 band + global) out of TMEM in ONE batch of tcgen05.ld, keeps them in registers for the max and
-// the exp pass, and dead blocks cost nothing on the CUDA cores.
+// warps owns exactly one block-row (TMEM lane quarter), so block sparsity is warp-uniform: a warp visits only its
+// LIVE slots (<= 4 band + global at window 4) in two rolled passes (row maximum, then exp2 + pack), re-reading the
+// scores from TMEM in the second pass, and dead blocks cost nothing on the CUDA cores.
+// This is the one-CTA-per-tile variant: it serves the wide windows (9..14 slots, 512 TMEM columns) and the debug
+// dumps; the default geometry runs the persistent kernel of attn_fwd_persist_sm100.cu (same arithmetic, bit for bit).
 // TMEM budget: S [0, 32*slots) ; P aliases S ; two O accumulators in dead S columns (the P V chain is split over two
 // issuing warps because one thread retires a TMEM-operand MMA only every ~123 cycles).  <= 256 columns -> two CTAs
 // per SM overlap each other's load / MMA / softmax / store phases.  The whole band arrives with ONE TMA box per
@@ -130,7 +132,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 4) {
     // ================= producer + MMA issuer: the whole warp runs this convergently, one lane is elected per op ====
     const int band_slots = ns - g.cls;
-    const int box1 = band_slots < 8 ? band_slots : 8;
     mbar_arrive_expect_tx_w(bar_qk, S::Q_BYTES + ns * S::SLOT_BYTES);
     tma_load_4d_w(sQ, &tmQ, bar_qk, 0, t * kTile, h, b);
     tma_load_4d_w(sK + g.cls * S::SLOT_BYTES, &tmKband, bar_qk, 0, band_lo * kBlock, h, b);    // OOB rows -> zeros
@@ -140,7 +141,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_load_4d_w(sV + g.cls * S::SLOT_BYTES, &tmVband, bar_v, 0, band_lo * kBlock, h, b);
     if (band_slots > 8) tma_load_4d_w(sV + (g.cls + 8) * S::SLOT_BYTES, &tmVband2, bar_v, 0, (band_lo + 8) * kBlock, h, b);
     if (g.cls) tma_load_4d_w(sV, &tmV, bar_v, 0, 0, h, b);
-    (void)box1;
     stamp(2);
 
     // ---- S = Q K^T : M = 128, N = 32*ns (split at 256), K = DH in steps of 16
