@@ -11,8 +11,9 @@
 //               time: S^T = K Q^T, dP^T = V dO^T (128 x 64), P^T / dS^T written over them as 16-bit, dV += P^T dO,
 //               dK += dS^T Q (A from TMEM; the dO / Q slots re-read MN-major from the SMEM the first MMAs read K-major).
 //
-// Both kernels need only 256 TMEM columns and <= 113 KB of shared memory, so two CTAs share an SM and overlap each
-// other's load / MMA / CUDA-core phases; within a CTA the tensor pipe runs the next chunk's S/dP while nothing else
+// Both kernels need only 256 TMEM columns and, for the default geometry (<= 8 key slots), <= 113 KB of shared memory,
+// so two CTAs share an SM and overlap each other's load / MMA / CUDA-core phases (windows 5..10: 14 slot buffers, one
+// CTA per SM); within a CTA the tensor pipe runs the next chunk's S/dP while nothing else
 // depends on it (tcgen05.mma executes in issue order, which also orders the in-place TMEM reuse between chunks).
 //
 // Reference: autograd of sdd -> softmax -> dsd, sparse_vae/core/sparse_matmul.py:463-488 (dV = P^T dO, dP = dO V^T,
@@ -27,13 +28,14 @@ using namespace ptx;
 
 long long* g_bwd_timeline = nullptr;   // debug only (svae_debug_set_bwd_timeline)
 
-constexpr int kBwdSlots = 8;
+constexpr int kBwdSlots = 8;          // key slots of the default geometry (two CTAs per SM)
+constexpr int kBwdSlotsWide = 14;     // windows 5..10: one CTA per SM
 constexpr int kBwdMathWarps = 8;                 // two warps per TMEM lane quarter: each owns 16 of a slot's 32 columns
 constexpr int kBwdThreads = (kBwdMathWarps + 1) * 32;   // + one TMA / MMA-issue warp
    // key slots per query tile (dQ pass); query slots per key tile <= 7
 
 // ------------------------------------------------------------------------------------------ dQ pass
-template <int DH>
+template <int DH, int NS>
 struct DqSmem {
   static constexpr int ROWB = DH * 2;
   static constexpr int TILE_BYTES = kTile * ROWB;
@@ -42,24 +44,27 @@ struct DqSmem {
   static constexpr int OFF_Q = OFF_DO + TILE_BYTES;        //   together the MN-major stacked operand [dO^T ; Q^T]
   static constexpr int OFF_O = OFF_Q + TILE_BYTES;         // O tile (delta), then [128 q][32 P_0 | 32 dS_0] (128-byte rows)
   static constexpr int OFF_K = OFF_O + TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + kBwdSlots * SLOT_BYTES;
-  static constexpr int OFF_BAR = OFF_V + kBwdSlots * SLOT_BYTES;
-  static constexpr int DYN_BYTES = OFF_BAR + 128;          // no alignment slack: the base is checked to be 1024-aligned
+  static constexpr int OFF_V = OFF_K + NS * SLOT_BYTES;
+  static constexpr int OFF_BAR = OFF_V + NS * SLOT_BYTES;
+  static constexpr int DYN_BYTES = OFF_BAR + 256;          // no alignment slack: the base is checked to be 1024-aligned
+  static constexpr int MAX_PASS = (NS + 2) / 3;
+  static constexpr int CTAS = NS <= 8 ? 2 : 1;
   static constexpr int PASS = 3;                           // slots per chunk
   static constexpr int COL_S = 0, COL_DP = 32 * PASS, COL_DQ = 64 * PASS, COL_G = 32 * PASS;
   static_assert(COL_DQ + DH <= 256 && COL_G + 64 <= COL_DQ, "TMEM plan");
-  static_assert(2 * (DYN_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+  static_assert(CTAS * (DYN_BYTES + 1024) <= 228 * 1024, "shared memory");
 };
 
-template <typename T, int DH>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+template <typename T, int DH, int NS>
+__global__ void __launch_bounds__(kBwdThreads, NS <= 8 ? 2 : 1)
 attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmKband,
-                         const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmDQ,
+                         const __grid_constant__ CUtensorMap tmVband, const __grid_constant__ CUtensorMap tmKband2,
+                         const __grid_constant__ CUtensorMap tmVband2, const __grid_constant__ CUtensorMap tmDQ,
                          const BwdParams p) {
   static_assert(DH == 64, "the stacked [dO^T ; Q^T] operand needs 2*DH == 128 rows");
-  using S = DqSmem<DH>;
+  using S = DqSmem<DH, NS>;
   constexpr int ROWB = S::ROWB;
   constexpr int PASS = S::PASS;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -68,9 +73,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sG = sO;                                         // reused once delta has been computed
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t *bar_ld = bars + 0, *bar_dq = bars + 1;
-  uint64_t* bar_sdp = bars + 2;                             // [3] MMA -> threads: chunk's S and dP are in TMEM
-  uint64_t* bar_ds = bars + 5;                              // [3] threads -> MMA: chunk's dS is in TMEM (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_sdp = bars + 2;                             // [MAX_PASS] MMA -> threads: chunk's S and dP are in TMEM
+  uint64_t* bar_ds = bars + 2 + S::MAX_PASS;                // [MAX_PASS] threads -> MMA: chunk's dS is in TMEM (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * S::MAX_PASS);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -102,7 +107,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (smem_u32(smem) & 1023u) __trap();     // dynamic shared memory must be 1024-byte aligned (SWIZZLE_128B)
       mbar_init(bar_ld, 1);
       mbar_init(bar_dq, 1);
-      for (int i = 0; i < 3; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, kBwdMathWarps * 32); }
+      for (int i = 0; i < S::MAX_PASS; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_ds + i, kBwdMathWarps * 32); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -112,6 +117,10 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     tma_load_4d_w(sO, &tmO, bar_ld, 0, t * kTile, h, b);
     tma_load_4d_w(sK, &tmKband, bar_ld, 0, band_lo * kBlock, h, b);   // OOB rows -> zeros
     tma_load_4d_w(sV, &tmVband, bar_ld, 0, band_lo * kBlock, h, b);
+    if (NS > 8 && g.nband > 8) {                                       // a TMA box holds at most 256 rows
+      tma_load_4d_w(sK + 8 * S::SLOT_BYTES, &tmKband2, bar_ld, 0, (band_lo + 8) * kBlock, h, b);
+      tma_load_4d_w(sV + 8 * S::SLOT_BYTES, &tmVband2, bar_ld, 0, (band_lo + 8) * kBlock, h, b);
+    }
     if (g.cls) {
       tma_load_4d_w(sK + g.nband * S::SLOT_BYTES, &tmK, bar_ld, 0, 0, h, b);
       tma_load_4d_w(sV + g.nband * S::SLOT_BYTES, &tmV, bar_ld, 0, 0, h, b);
@@ -152,7 +161,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_ds + c, 0);
         tc_fence_after();
-        stamp(4 + 2 * c);
+        if (c < 3) stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {     // dQ += dS_j K_j
           const int j = order(c * PASS + i);
           if (!slot_valid(j)) continue;
@@ -178,7 +187,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
           tc_commit_w(bar_dq);
         }
-        stamp(5 + 2 * c);
+        if (c < 3) stamp(5 + 2 * c);
       }
     }
     __syncwarp();
@@ -234,7 +243,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int c = 0; c < npass; ++c) {
       mbar_wait(bar_sdp + c, 0);
       tc_fence_after();
-      stamp(3 + 2 * c);
+      if (c < 3) stamp(3 + 2 * c);
       bool wrote_g = false;
       for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {
         const int j = order(c * PASS + i);
@@ -303,7 +312,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_ds + c);
-      stamp(4 + 2 * c);
+      if (c < 3) stamp(4 + 2 * c);
     }
 
     mbar_wait(bar_dq, 0);
@@ -352,12 +361,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------ dK/dV pass
-template <int DH>
+template <int DH, int NQ_>
 struct DkvSmem {
   static constexpr int ROWB = DH * 2;
   static constexpr int TILE_BYTES = kTile * ROWB;
   static constexpr int SLOT_BYTES = kBlock * ROWB;
-  static constexpr int NQ = kBwdSlots - 1;              // query-block slots (left + 3 + nsup <= 7)
+  static constexpr int NQ = NQ_;                        // query-block slots (left + 3 + nsup)
+  static constexpr int MAX_PASS = (NQ + 1) / 2;
+  static constexpr int CTAS = NQ <= 7 ? 2 : 1;
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE_BYTES;
   static constexpr int OFF_Q = OFF_V + TILE_BYTES;
@@ -365,19 +376,20 @@ struct DkvSmem {
   static constexpr int OFF_LSE = OFF_DO + NQ * SLOT_BYTES;          // -lse * log2(e) per query column
   static constexpr int OFF_DELTA = OFF_LSE + NQ * kBlock * 4;       // -delta * scale per query column
   static constexpr int OFF_BAR = OFF_DELTA + NQ * kBlock * 4;
-  static constexpr int DYN_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int DYN_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int PASS = 2;
   static constexpr int COL_ST = 0, COL_DPT = 64, COL_DV = 128, COL_DK = 192;
-  static_assert(2 * (DYN_BYTES + 1024) <= 228 * 1024, "two CTAs per SM");
+  static_assert(CTAS * (DYN_BYTES + 1024) <= 228 * 1024, "shared memory");
 };
 
-template <typename T, int DH>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename T, int DH, int NQ>
+__global__ void __launch_bounds__(kThreads, NQ <= 7 ? 2 : 1)
 attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmQband, const __grid_constant__ CUtensorMap tmDOband,
+                          const __grid_constant__ CUtensorMap tmQband2, const __grid_constant__ CUtensorMap tmDOband2,
                           const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
                           const BwdParams p) {
-  using S = DkvSmem<DH>;
+  using S = DkvSmem<DH, NQ>;
   constexpr int ROWB = S::ROWB;
   constexpr int PASS = S::PASS;
   extern __shared__ uint8_t smem_raw[];
@@ -387,9 +399,9 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   float* sNegDelta = reinterpret_cast<float*>(smem + S::OFF_DELTA);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t *bar_ld = bars + 0, *bar_out = bars + 1;
-  uint64_t* bar_sdp = bars + 2;     // [4]
-  uint64_t* bar_pds = bars + 6;     // [4], 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_sdp = bars + 2;                       // [MAX_PASS]
+  uint64_t* bar_pds = bars + 2 + S::MAX_PASS;         // [MAX_PASS], 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * S::MAX_PASS);
 
   const int warp = warp_index(), lane = threadIdx.x & 31;
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -411,7 +423,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     if (lane == 0) {
       mbar_init(bar_ld, 1);
       mbar_init(bar_out, 1);
-      for (int i = 0; i < 4; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_pds + i, 128); }
+      for (int i = 0; i < S::MAX_PASS; ++i) { mbar_init(bar_sdp + i, 1); mbar_init(bar_pds + i, 128); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -420,6 +432,10 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     tma_load_4d_w(sV, &tmV, bar_ld, 0, t * kTile, h, b);
     tma_load_4d_w(sQ, &tmQband, bar_ld, 0, q_lo * kBlock, h, b);      // rows outside [0, L) -> zeros
     tma_load_4d_w(sDO, &tmDOband, bar_ld, 0, q_lo * kBlock, h, b);
+    if (NQ > 8 && nq > 8) {                                            // a TMA box holds at most 256 rows
+      tma_load_4d_w(sQ + 8 * S::SLOT_BYTES, &tmQband2, bar_ld, 0, (q_lo + 8) * kBlock, h, b);
+      tma_load_4d_w(sDO + 8 * S::SLOT_BYTES, &tmDOband2, bar_ld, 0, (q_lo + 8) * kBlock, h, b);
+    }
     tmem_alloc<256>(tmem_slot);
   }
   tc_fence_before();
@@ -453,7 +469,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_pds + c, 0);
         tc_fence_after();
-        stamp(4 + 2 * c);
+        if (c < 4) stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < nq; ++i) {
           const int slot = c * PASS + i;
 #pragma unroll
@@ -472,7 +488,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         } else {
           tc_commit_w(bar_out);
         }
-        stamp(5 + 2 * c);
+        if (c < 4) stamp(5 + 2 * c);
       }
     }
     __syncwarp();
@@ -509,7 +525,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     for (int cpass = 0; cpass < npass; ++cpass) {
       mbar_wait(bar_sdp + cpass, 0);
       tc_fence_after();
-      stamp(3 + 2 * cpass);
+      if (cpass < 4) stamp(3 + 2 * cpass);
       for (int i = 0; i < PASS && cpass * PASS + i < nq; ++i) {
         const int slot = cpass * PASS + i;
         uint32_t pk[16], dsk[16];
@@ -546,7 +562,7 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_pds + cpass);
-      stamp(4 + 2 * cpass);
+      if (cpass < 4) stamp(4 + 2 * cpass);
     }
 
     mbar_wait(bar_out, 0);
@@ -599,7 +615,7 @@ bool bwd_supported(const svae_attn_desc* d) {
   if (d->dtype != SVAE_DTYPE_BF16 && d->dtype != SVAE_DTYPE_F16) return false;
   if (d->head_dim != 64 || !(d->scale > 0.f)) return false;
   const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
-  return g.nslots <= kBwdSlots && g.nband <= kBwdSlots - 1;
+  return g.nslots <= kBwdSlotsWide && g.nband <= kBwdSlotsWide - 1;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -610,7 +626,7 @@ size_t bwd_workspace(const svae_attn_desc* d) {
   return stats + gacc;
 }
 
-template <typename T, int DH>
+template <typename T, int DH, int NS>
 static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const void* out,
                       const void* dout, const float* lse, const float* kpm, void* dq, void* dk, void* dv,
                       void* workspace, cudaStream_t st) {
@@ -628,9 +644,12 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
   p.scale = d->scale; p.scale_log2 = d->scale * kLog2e;
 
   const CUtensorMapDataType dt = Elem<T>::tm;
-  CUtensorMap tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tDQ128, tK128, tV128, tQband, tDOband, tDK128, tDV128;
+  CUtensorMap tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tKband2, tVband2, tDQ128, tK128, tV128, tQband, tDOband,
+      tQband2, tDOband2, tDK128, tDV128;
   int rc;
-  const int band_rows = g.nband * kBlock;      // <= 224
+  // the band arrives with one TMA box of <= 8 blocks (256 rows) plus, for the wide windows, a second box with the rest
+  const int band_rows = (g.nband <= 8 ? g.nband : 8) * kBlock;
+  const int band2_rows = (g.nband > 8 ? g.nband - 8 : 1) * kBlock;
 #define SVAE_TM(map, ptr, strd, rows) \
   if ((rc = encode_tmap(&map, dt, ptr, DH, L, H, B, strd, rows))) return rc
   SVAE_TM(tQ128, q, d->q_stride, kTile);         SVAE_TM(tDO128, dout, d->do_stride, kTile);
@@ -640,25 +659,29 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
   SVAE_TM(tK128, k, d->k_stride, kTile);         SVAE_TM(tV128, v, d->v_stride, kTile);
   SVAE_TM(tQband, q, d->q_stride, band_rows);    SVAE_TM(tDOband, dout, d->do_stride, band_rows);
   SVAE_TM(tDK128, dk, d->dk_stride, kTile);      SVAE_TM(tDV128, dv, d->dv_stride, kTile);
+  SVAE_TM(tKband2, k, d->k_stride, band2_rows);  SVAE_TM(tVband2, v, d->v_stride, band2_rows);
+  SVAE_TM(tQband2, q, d->q_stride, band2_rows);  SVAE_TM(tDOband2, dout, d->do_stride, band2_rows);
 #undef SVAE_TM
 
-  auto kq = attn_bwd_dq_sm100_kernel<T, DH>;
-  auto kkv = attn_bwd_dkv_sm100_kernel<T, DH>;
-  static bool configured = false;
+  using SQ = DqSmem<DH, NS>;
+  using SKV = DkvSmem<DH, NS - 1>;
+  auto kq = attn_bwd_dq_sm100_kernel<T, DH, NS>;
+  auto kkv = attn_bwd_dkv_sm100_kernel<T, DH, NS - 1>;
+  static bool configured = false;       // per template instantiation
   if (!configured) {
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem<DH>::DYN_BYTES));
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem<DH>::DYN_BYTES));
+    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ::DYN_BYTES));
+    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, SKV::DYN_BYTES));
     configured = true;
   }
   dim3 grid((L + kTile - 1) / kTile, H, B);
   {
     ScopedKernelTimer timer("attn_bwd_dq_sm100", st);
-    kq<<<grid, kBwdThreads, DqSmem<DH>::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tDQ128, p);
+    kq<<<grid, kBwdThreads, SQ::DYN_BYTES, st>>>(tQ128, tDO128, tO128, tK32, tV32, tKband, tVband, tKband2, tVband2, tDQ128, p);
   }
   SVAE_CUDA_CHECK(cudaGetLastError());
   {
     ScopedKernelTimer timer("attn_bwd_dkv_sm100", st);
-    kkv<<<grid, kThreads, DkvSmem<DH>::DYN_BYTES, st>>>(tK128, tV128, tQband, tDOband, tDK128, tDV128, p);
+    kkv<<<grid, kThreads, SKV::DYN_BYTES, st>>>(tK128, tV128, tQband, tDOband, tQband2, tDOband2, tDK128, tDV128, p);
   }
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
@@ -666,8 +689,13 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
 
 int bwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const void* out, const void* dout,
         const float* lse, const float* kpm, void* dq, void* dk, void* dv, void* workspace, cudaStream_t st) {
-  if (d->dtype == SVAE_DTYPE_BF16) return launch_bwd<__nv_bfloat16, 64>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
-  return launch_bwd<__half, 64>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
+  const TileGeom g = make_geom(d->window_size, d->causal, d->include_cls, d->seq_len / d->block_size);
+  const bool small = g.nslots <= kBwdSlots && g.nband <= kBwdSlots - 1;      // two CTAs per SM
+  if (d->dtype == SVAE_DTYPE_BF16)
+    return small ? launch_bwd<__nv_bfloat16, 64, kBwdSlots>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st)
+                 : launch_bwd<__nv_bfloat16, 64, kBwdSlotsWide>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
+  return small ? launch_bwd<__half, 64, kBwdSlots>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st)
+               : launch_bwd<__half, 64, kBwdSlotsWide>(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
 }
 
 }  // namespace sm100
