@@ -114,3 +114,24 @@ def test_fused_ce_rejects_cpu():
     from sparse_vae_b200.core.fused_ce import fused_vocab_nll
     with pytest.raises(ValueError):
         fused_vocab_nll(torch.randn(1, 4, 8), torch.nn.Linear(8, 8192), torch.ones(1, 3, dtype=torch.long))
+
+
+def test_fused_ce_fp16_autocast():
+    """fp16 (the reference's own `precision=16`): same contract as bf16, tighter mantissa."""
+    from sparse_vae_b200.core.fused_ce import fused_vocab_nll
+    B, L, D, V = 2, 257, 256, 16384
+    hidden, weight, bias, labels = _setup(B, L, D, V, seed=9, pad_from=[256, 100])
+    lin = torch.nn.Linear(D, V).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(weight); lin.bias.copy_(bias)
+    h = hidden.cuda().requires_grad_(True)
+    with torch.autocast('cuda', dtype=torch.float16):
+        loss = fused_vocab_nll(h, lin, labels.cuda())
+    loss.backward()
+    hd, wd, bd = (t.double().requires_grad_(True) for t in (hidden, weight, bias))
+    ref = _reference_nll(hd, wd, bd, labels)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-3 * abs(ref.item())
+    assert (h.grad.double().cpu() - hd.grad).abs().max() <= 1e-2 * hd.grad.abs().max()
+    assert (lin.weight.grad.double().cpu() - wd.grad).abs().max() <= 1e-2 * wd.grad.abs().max()
+    assert (lin.bias.grad.double().cpu() - bd.grad).abs().max() <= 1e-2 * bd.grad.abs().max()
