@@ -21,6 +21,11 @@ ATTN_PERSISTENT_DEFAULT = True       # persistent warp-specialised forward (95 u
 BOTTLENECK_WORKSPACE_BYTES = 8448
 ABI_VERSION = 1
 
+# Switch for the rows beyond the attention / bottleneck kernels (rotary, LayerNorm, Linear bias gradient, fused
+# vocabulary cross-entropy, fused clipping + RAdam, in-place latent row).  False selects the reference's literal torch op
+# sequence for those rows (still on the GPU); tests/test_gpu_training_curve.py trains both ways and compares the curves.
+FUSED_EXTRAS = True
+
 _TORCH_TO_SVAE = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
 
 EXPORTS = (

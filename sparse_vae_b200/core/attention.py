@@ -84,7 +84,7 @@ def encode_position_rotary(x: Tensor, start: int = 0, max_pos: int = 10000) -> T
     the autocast dtype at once; the kernel returns that rounded tensor directly.
     """
     half = x.shape[-1] // 2
-    if (x.is_cuda and x.ndim >= 2 and x.shape[-1] % 8 == 0 and x.numel() > 0
+    if (N.FUSED_EXTRAS and x.is_cuda and x.ndim >= 2 and x.shape[-1] % 8 == 0 and x.numel() > 0
             and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
         cos, sin = _cached_tables(x.shape[-2], half, start, max_pos, x.dtype, x.device)
         if cos.dtype == x.dtype or cos.dtype == torch.float32:

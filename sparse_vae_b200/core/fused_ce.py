@@ -22,7 +22,7 @@ ROW_CHUNK = 4096
 
 
 def supported(hidden: Tensor, linear: nn.Linear) -> bool:
-    return bool(hidden.is_cuda and linear.weight.is_cuda and N.lib.svae_vocab_ce_supported(linear.out_features))
+    return bool(N.FUSED_EXTRAS and hidden.is_cuda and linear.weight.is_cuda and N.lib.svae_vocab_ce_supported(linear.out_features))
 
 
 def _token_weights(labels: Tensor, vocab: int, ignore_index: int = 0) -> Tensor:
@@ -107,7 +107,7 @@ def fused_vocab_nll(hidden: Tensor, linear: nn.Linear, labels: Tensor, row_chunk
     (the reference's next-token objective: position s predicts token s+1; padding id 0 ignored)."""
     B, L, _ = hidden.shape
     assert labels.shape == (B, L - 1), "labels must be the tokens shifted by one"
-    if not supported(hidden, linear):
+    if not (hidden.is_cuda and linear.weight.is_cuda and N.lib.svae_vocab_ce_supported(linear.out_features)):
         raise ValueError("fused_vocab_nll needs CUDA tensors and a vocabulary of 8192*k (k <= 4) entries")
     token_w = _token_weights(labels, linear.out_features)
     # the last position predicts nothing: label 0 / weight 0 instead of slicing (no copy, no zero-padded backward)

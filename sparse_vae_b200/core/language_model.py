@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn, Tensor
 from torch.optim.lr_scheduler import LambdaLR
 
+from .. import _native as N
 from .lightning_shim import DictConfig, LightningModule
 from .padded_tensor import PaddedTensor
 from .rectified_adam import RAdam
@@ -93,7 +94,7 @@ class LanguageModel(LightningModule, ABC):
 
     def on_after_backward(self):
         grads = [p.grad for p in self.parameters() if p.grad is not None]
-        if grads and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in grads):
+        if N.FUSED_EXTRAS and grads and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in grads):
             # one fused multi-tensor pass (csrc/optim.cu) instead of a per-parameter norm + scale
             if getattr(self, '_fused_clipper', None) is None:
                 from ..fused_optim import FusedGradClipper

@@ -65,7 +65,7 @@ class LayerNorm(nn.LayerNorm):
     emit_autocast_dtype: bool = True
 
     def forward(self, x: Tensor) -> Tensor:
-        fused = (x.is_cuda and self.elementwise_affine and len(self.normalized_shape) == 1 and x.numel() > 0
+        fused = (N.FUSED_EXTRAS and x.is_cuda and self.elementwise_affine and len(self.normalized_shape) == 1 and x.numel() > 0
                  and self.weight.dtype == torch.float32 and N.lib.svae_layernorm_supported(x.shape[-1]))
         if fused:
             out_dtype = x.dtype

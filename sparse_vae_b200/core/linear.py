@@ -57,7 +57,7 @@ class _LinearFn(torch.autograd.Function):
 
 class Linear(nn.Linear):
     def forward(self, x: Tensor) -> Tensor:
-        if (x.is_cuda and self.bias is not None and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
+        if (N.FUSED_EXTRAS and x.is_cuda and self.bias is not None and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
                 and self.out_features % 8 == 0 and x.numel() >= _MIN_ROWS * self.in_features
                 and (x.requires_grad or self.weight.requires_grad)):
             dtype = torch.get_autocast_dtype('cuda')

@@ -9,6 +9,8 @@ from __future__ import annotations
 import torch
 from torch.optim import Optimizer
 
+from .. import _native as N
+
 
 class RAdam(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=1e-6, lamb=False):
@@ -56,7 +58,7 @@ class RAdam(Optimizer):
                 group['step'] += 1
                 continue
 
-            if not group['lamb'] and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            if N.FUSED_EXTRAS and not group['lamb'] and all(p.is_cuda and p.dtype == torch.float32 for p in params):
                 from ..fused_optim import FusedRAdamStep
                 cache = self.__dict__.setdefault('_fused_steps', {})     # kept off param_groups (state_dict stays clean)
                 fused = cache.get(id(group))

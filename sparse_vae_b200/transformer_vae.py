@@ -16,6 +16,7 @@ from torch.utils.checkpoint import checkpoint
 from .core.attention import Attention, Perceiver
 from .core.conditional_gaussian import ConditionalGaussian
 from .core.continuous_autoencoder import ContinuousVAE, ContinuousVAEHparams
+from . import _native as N
 from .core import fused_ce
 from .core.generation import GenerationState
 from .core.lightning_shim import DictConfig
@@ -127,7 +128,7 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         padding = x_pad if padding is None else padding
         use_checkpoint = self.hparams.grad_checkpointing and x.requires_grad
         for i, (layer, project) in enumerate(zip(self.decoder_layers, self.z_projections)):
-            if i > 0 and x.is_cuda and x.requires_grad and not x.is_leaf and not use_checkpoint:
+            if N.FUSED_EXTRAS and i > 0 and x.is_cuda and x.requires_grad and not x.is_leaf and not use_checkpoint:
                 x = _ReplaceFirstPosition.apply(x, project(z).to(x.dtype))       # x is the previous layer's own output
             else:
                 x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)   # z takes the [CLS] position
