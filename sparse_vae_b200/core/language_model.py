@@ -19,7 +19,6 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from .. import _native as N
 from .lightning_shim import DictConfig, LightningModule
-from .padded_tensor import PaddedTensor
 from .rectified_adam import RAdam
 
 

@@ -16,7 +16,7 @@ from .language_model import LanguageModel, LanguageModelHparams
 from .layer_norm import LayerNorm
 from .linear import Linear
 from .lightning_shim import DictConfig
-from .padded_tensor import PaddedTensor, split_padding
+from .padded_tensor import split_padding
 from .rotary_embedding import RotaryEmbedding
 
 VOCAB_SIZE = 2 ** 15

@@ -21,7 +21,7 @@ from .core import fused_ce
 from .core.generation import GenerationState
 from .core.lightning_shim import DictConfig
 from .core.math_utils import marginal_kl
-from .core.padded_tensor import PaddedTensor, split_padding
+from .core.padded_tensor import split_padding
 from .core.transformer_language_model import TransformerHparams, TransformerLanguageModel
 
 
