@@ -10,7 +10,8 @@ bucket's last gradient has been written, and launches the bucket's asynchronous 
 communication overlaps the rest of backward; afterwards every `.grad` is a view into its bucket.  With one process
 there is nothing to reduce and the gradients stay where autograd put them.  Parameters that never receive a gradient (the
 reference's unused `pos_linear` layers, core/attention.py:39) are discovered on the first step and left out.
-Gradient clipping must run after `finish()`.
+Gradient clipping must run after `finish()`.  With gradient accumulation set `reducer.sync = False` for every
+micro-batch but the last one (the hooks fire on every backward).
 """
 from __future__ import annotations
 
@@ -72,9 +73,12 @@ class GradientAllReducer:
                          for p in module.parameters() if p.requires_grad]
         self._built = False
         self._reduced_numel = 0
+        self.sync = True        # set False for all but the last micro-batch of a gradient-accumulation step
 
     # ---- hooks ----------------------------------------------------------------------------------
     def _on_grad(self, p: nn.Parameter):
+        if not self.sync:                     # gradients keep accumulating locally; reduce on the last micro-batch
+            return
         if not self._built:
             self._ready_order.append(p)
             return

@@ -50,7 +50,14 @@ def _worker(rank, world, port, out):
         y = torch.randn(world * 6, 4, generator=g)
         xs, ys = x[rank * 6:(rank + 1) * 6], y[rank * 6:(rank + 1) * 6]
         reducer.zero_grad()
-        ((model(xs) - ys) ** 2).mean().backward()
+        if step % 2:                              # gradient accumulation over two micro-batches: reduce after the last one
+            half = xs.shape[0] // 2
+            reducer.sync = False
+            (((model(xs[:half]) - ys[:half]) ** 2).mean() / 2).backward()
+            reducer.sync = True
+            (((model(xs[half:]) - ys[half:]) ** 2).mean() / 2).backward()
+        else:
+            ((model(xs) - ys) ** 2).mean().backward()
         reducer.finish()
         ref.zero_grad(set_to_none=True)
         ((ref(x) - y) ** 2).mean().backward()                       # global batch on one process

@@ -65,6 +65,7 @@ def main(args):
     for step in range(config.trainer.max_steps):
         reducer.zero_grad()
         for micro in range(accum):
+            reducer.sync = micro == accum - 1            # all-reduce only once the last micro-batch has been accumulated
             batch = to_device(synthetic_tokens(batch_size, seq_len, seed=7295 + 131 * step + micro + 7919 * rank), device)
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 loss = model.training_step(batch, step)['loss'] / accum
@@ -76,7 +77,7 @@ def main(args):
         model.global_step += 1
         if rank == 0:
             logged = {k: round(float(v), 4) for k, v in model.logged.items()}
-            print(f"step {step}: loss {float(loss) * accum:.4f} {logged}")
+            print(f"step {step}: loss {float(loss.detach()) * accum:.4f} {logged}")
 
 
 if __name__ == '__main__':
