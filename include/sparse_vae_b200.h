@@ -219,6 +219,25 @@ SVAE_API int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, 
 SVAE_API int svae_rotary(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype,
                 int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, void* stream);
 
+/* ---- token-by-token decoding ----------------------------------------------------------------
+ * One sparse-attention layer's step of TransformerVAE.sample (reference transformer_vae.py:112-126 ->
+ * core/attention.py:60-100 with the KV cache of :107-142): rotary position encoding of the new q / k rows at the
+ * position read from the DEVICE counter `position` (so the call can be replayed inside a CUDA graph), append of
+ * k / v to the caches, and attention of the new query over the visible keys.
+ *   q, k, v               [B, H*head_dim] `dtype`, `in_stride` elements between samples (slices of one fused
+ *                         [B, 3*H*head_dim] projection are fine); out [B, H*head_dim] contiguous
+ *   cos_table, sin_table  [table_rows, H*head_dim/2] fp32, row p = position p (positions >= table_rows clamp)
+ *   key_cache, value_cache[B, (window+1)*block, H*head_dim] `dtype`: slots [0, block) = positions 0..block-1, the
+ *                         rest a ring over later positions; identical to the reference's cache while
+ *                         position < (window+1)*block, so the first tokens may be decoded by the ATen path.
+ * Visible keys = block 0 and key blocks max(1, b-window+1)..b of the current block b = position / block, i.e.
+ * the causal include_cls rows of svae_layout_build. */
+SVAE_API int svae_decode_attn_supported(int32_t head_dim, int32_t window, int32_t block);
+SVAE_API int svae_decode_attn(const void* q, const void* k, const void* v, const float* cos_table,
+                     const float* sin_table, void* key_cache, void* value_cache, void* out,
+                     const int32_t* position, int32_t B, int32_t H, int32_t head_dim, int32_t window, int32_t block,
+                     int32_t table_rows, int64_t in_stride, int32_t dtype, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

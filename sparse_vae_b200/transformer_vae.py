@@ -17,7 +17,7 @@ from .core.attention import Attention, Perceiver
 from .core.conditional_gaussian import ConditionalGaussian
 from .core.continuous_autoencoder import ContinuousVAE, ContinuousVAEHparams
 from . import _native as N
-from .core import fused_ce
+from .core import decode, fused_ce
 from .core.generation import GenerationState
 from .core.lightning_shim import DictConfig
 from .core.math_utils import marginal_kl
@@ -151,6 +151,7 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         state = GenerationState(max_length, batch_size, self.start_token, self.end_token, device=self.device, **kwargs)
         state.current_index = 1
         state.output_ids[:, 0] = self.start_token
+        graphed = decode.supported(self, state)
         with Attention.kv_cache(max_length):
             while not state.should_stop():
                 x = self.input_layer(state.prev_tokens())
@@ -159,4 +160,7 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
                         x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)
                     x = layer(x)
                 Attention.update_kv_cache(state.process_logits(self.output_layer(x.squeeze(1))))
+                if graphed:                 # position 0 (the z row) is done; every later token is one graph replay
+                    decode.GraphedDecoder(self, state, decode.TRACE).run()
+                    break
         return state.final_output()
