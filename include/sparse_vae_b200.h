@@ -238,6 +238,18 @@ SVAE_API int svae_decode_attn(const void* q, const void* k, const void* v, const
                      const int32_t* position, int32_t B, int32_t H, int32_t head_dim, int32_t window, int32_t block,
                      int32_t table_rows, int64_t in_stride, int32_t dtype, float scale, void* stream);
 
+/* One-launch restatement of GenerationState.process_logits with its default settings (reference
+ * core/generation.py:40-72): repetition penalty over the last `penalty_window` generated tokens, temperature, nucleus
+ * filtering (largest set of most likely tokens with mass <= top_p, never empty), one categorical draw per row by
+ * inverse CDF from uniforms[b] in [0, 1), then the bookkeeping of :66-71: ids[b, *column] = token if alive[b];
+ * alive[b] cleared and *finished incremented when the token is end_token.
+ *   logits [B, vocab] 16-bit, contiguous (not modified); ids [B, ids_stride] int64; column: device scalar. */
+SVAE_API int svae_sample_top_p_supported(int32_t vocab, int32_t dtype);
+SVAE_API int svae_sample_top_p(const void* logits, int32_t dtype, int32_t B, int32_t vocab, int64_t* ids, int64_t ids_stride,
+                      const int64_t* column, const float* uniforms, uint8_t* alive, int32_t* finished,
+                      int32_t penalty_window, float repetition_penalty, float temperature, float top_p,
+                      int64_t end_token, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

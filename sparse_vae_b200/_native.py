@@ -36,7 +36,7 @@ EXPORTS = (
     'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
-    'svae_decode_attn_supported', 'svae_decode_attn',
+    'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
 )
 
 
@@ -126,6 +126,10 @@ def _load() -> C.CDLL:
     lib.svae_decode_attn_supported.argtypes = [i32, i32, i32]
     lib.svae_decode_attn.restype = C.c_int
     lib.svae_decode_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i32, C.c_float, vp]
+    lib.svae_sample_top_p_supported.restype = C.c_int
+    lib.svae_sample_top_p_supported.argtypes = [i32, i32]
+    lib.svae_sample_top_p.restype = C.c_int
+    lib.svae_sample_top_p.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, i64, vp]
     lib.svae_debug_set_bwd_timeline.restype = None
     lib.svae_debug_set_bwd_timeline.argtypes = [vp]
     lib.svae_debug_pipe_bench.restype = C.c_int

@@ -11,11 +11,14 @@ whole decoder is ONE graph replay:
     attention over the visible keys; q / k / v come from one fused [3D, D] projection;
   * `GenerationState.process_logits` is restated with fixed shapes (same ops, same order, same RNG consumption).
 
-Semantics kept from the reference: finished samples leave the batch (their cache rows are dropped and the rest is
-compacted, `Attention.update_kv_cache`), so the random stream of `multinomial` sees the same live batch as the
-reference's; the graph is re-captured for the smaller batch when that happens.  The first token (position 0, where
-every layer's input is its own projection of z) runs through the unfused modules.  Weights are frozen while sampling:
-they are cast to the autocast dtype once per call instead of once per token.
+  * with the reference's default settings (nucleus sampling) the sampler itself is one launch (csrc/sampling.cu):
+    threshold search instead of a full sort; same token distribution, its own use of the random stream.
+
+Finished samples leave the batch like in the reference (their cache rows are dropped and the rest is compacted,
+`Attention.update_kv_cache`) -- but not after every token: they first stay behind as dead rows (nothing written, not
+counted again) and the batch is compacted and the graph re-captured once a quarter of it is dead (`COMPACT_BELOW`).
+The first token (position 0, where every layer's input is its own projection of z) runs through the unfused modules.
+Weights are frozen while sampling: they are cast to the autocast dtype once per call instead of once per token.
 """
 from __future__ import annotations
 
@@ -31,6 +34,9 @@ from .generation import GenerationState
 
 PENALTY_WINDOW = 512            # core/generation.py:44 -- repetition penalty looks at the last 512 tokens
 TRACE: Optional[list] = None    # tests: set to a list to receive (live row indices, logits) of every graphed step
+# Finished samples are dropped from the batch (reference: after every token, core/attention.py:164-168) once the live
+# ones are at most this fraction of the captured batch; 1.0 = compact (and re-capture) whenever a sample finishes.
+COMPACT_BELOW = 0.75
 
 
 def supported(model, state: GenerationState) -> bool:
@@ -90,10 +96,15 @@ class GraphedDecoder:
         self.finished = torch.zeros(1, dtype=torch.int32, device=dev)
         self.finished_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.trace = trace_logits
+        vocab = self.head_w3.shape[0]
+        # the reference's default decoding (nucleus sampling, no top-k) has a one-launch sampler; greedy / top-k
+        # decoding keeps the ATen op sequence of core/generation.py
+        self.fused_sampler = bool(state.temperature > 0.0 and state.top_k == 0 and self.dtype != torch.float32 and
+                                  N.lib.svae_sample_top_p_supported(vocab, N.svae_dtype(self.dtype)))
         self.graph = None
         self.rows = None            # indices of the live samples in state.output_ids
         self.ids = None             # [live, max_length] working copy of their rows
-        self.continuing = None      # [live] bool, result of the last step
+        self.alive = None           # [captured batch] bool: still generating
         self.replays = 0
         self.captures = 0
 
@@ -156,10 +167,23 @@ class GraphedDecoder:
         logits = F.linear(h, self.head_w3, self.head_b3)
         if self.trace is not None:
             self.trace_buffer.copy_(logits)
-        ids = self._process_logits(logits)
-        self.ids.scatter_(1, self.column.expand(B, 1), ids[:, None])
-        torch.ne(ids, self.state.end_token, out=self.continuing)
-        self.finished.copy_((~self.continuing).sum())
+            self.trace_alive.copy_(self.alive)
+        st = self.state
+        if self.fused_sampler:
+            self.finished.zero_()
+            uniforms = torch.rand(B, device=logits.device)
+            N.check(N.lib.svae_sample_top_p(logits.data_ptr(), N.svae_dtype(logits.dtype), B, logits.shape[1],
+                                            self.ids.data_ptr(), self.ids.stride(0), self.column.data_ptr(),
+                                            uniforms.data_ptr(), self.alive.data_ptr(), self.finished.data_ptr(),
+                                            PENALTY_WINDOW, float(max(st.repetition_penalty, 1.0)), float(st.temperature),
+                                            float(st.top_p), int(st.end_token), N.current_stream(logits.device)),
+                    'svae_sample_top_p')
+        else:
+            ids = self._process_logits(logits)
+            self.ids.scatter_(1, self.column.expand(B, 1), torch.where(self.alive, ids, 0)[:, None])
+            ended = self.alive & (ids == st.end_token)
+            self.finished.copy_(ended.sum())
+            self.alive &= ~ended
         self.position += 1
         self.column += 1
 
@@ -168,12 +192,13 @@ class GraphedDecoder:
         st = self.state
         self.rows = st.live_sample_mask.nonzero().flatten()
         self.ids = st.output_ids[self.rows].contiguous()
-        self.continuing = torch.ones(self.rows.numel(), dtype=torch.bool, device=self.ids.device)
+        self.alive = torch.ones(self.rows.numel(), dtype=torch.bool, device=self.ids.device)
         self.position.fill_(st.current_index - 1)
         self.column.fill_(st.current_index)
         if self.trace is not None:
             self.trace_buffer = torch.empty(self.rows.numel(), self.head_w3.shape[0], dtype=self.dtype,
                                             device=self.ids.device)
+            self.trace_alive = torch.ones_like(self.alive)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         with torch.cuda.graph(self.graph):
@@ -185,8 +210,8 @@ class GraphedDecoder:
         st = self.state
         st.output_ids[self.rows] = self.ids
         if drop_finished:
-            st.live_sample_mask[self.rows] = self.continuing
-            Attention.update_kv_cache(self.continuing)
+            st.live_sample_mask[self.rows] = self.alive
+            Attention.update_kv_cache(self.alive)
         self.graph = None
 
     @torch.no_grad()
@@ -203,12 +228,17 @@ class GraphedDecoder:
             stream.synchronize()
             st.current_index += 1
             if self.trace is not None:
-                self.trace.append((self.rows.clone(), self.trace_buffer.clone()))
+                self.trace.append((self.rows[self.trace_alive], self.trace_buffer[self.trace_alive]))
             done = int(self.finished_host[0])
             if done:
                 live -= done
-                self._retire(drop_finished=True)
+                # finished samples stay in the captured batch as dead rows (no writes, not counted again) until enough
+                # of them have piled up to pay for compacting the caches and capturing a smaller graph
+                if live and live <= COMPACT_BELOW * self.rows.numel():
+                    self._retire(drop_finished=True)
         if self.graph is not None:
-            self._retire(drop_finished=False)
+            self._retire(drop_finished=live > 0)
+            if live == 0:
+                st.live_sample_mask[self.rows] = False
         for module in Attention.live_attention_modules or ():
             module.cache_index = st.current_index - 1

@@ -172,3 +172,115 @@ def test_greedy_graphed_sampler_equals_module_sampler():
     same_prefix = (fast == slow).long().cumprod(dim=1).sum(dim=1)
     assert (same_prefix >= 8).all(), same_prefix              # decoding agrees until a near-tie (if any) flips a token
     assert (same_prefix == fast.shape[1]).float().mean() >= 0.5, same_prefix
+
+
+# ---------------------------------------------------------------- one-launch nucleus sampler (csrc/sampling.cu)
+def _run_sampler(logits, uniforms, ids=None, column=1, alive=None, penalty=1.0, temperature=1.0, top_p=0.9, end_token=2):
+    from sparse_vae_b200 import _native as N
+    B, V = logits.shape
+    dev = logits.device
+    ids = torch.zeros(B, 8, dtype=torch.long, device=dev) if ids is None else ids
+    alive = torch.ones(B, dtype=torch.bool, device=dev) if alive is None else alive
+    finished = torch.zeros(1, dtype=torch.int32, device=dev)
+    col = torch.full((1, 1), column, dtype=torch.long, device=dev)
+    N.check(N.lib.svae_sample_top_p(logits.data_ptr(), N.svae_dtype(logits.dtype), B, V, ids.data_ptr(), ids.stride(0),
+                                    col.data_ptr(), uniforms.data_ptr(), alive.data_ptr(), finished.data_ptr(), 512,
+                                    penalty, temperature, top_p, end_token, N.current_stream(dev)), 'svae_sample_top_p')
+    return ids, alive, int(finished.item())
+
+
+def _nucleus_weights(x64, top_p):
+    """The kernel's rule in float64 on the CPU: keep the most likely values while their mass stays <= top_p, admit
+    boundary ties in index order while they fit, never keep nothing.  x64: [V] float64 (exactly representable logits)."""
+    e = torch.exp(x64 - x64.max())
+    budget = top_p * e.sum()
+    keep = torch.zeros_like(e, dtype=torch.bool)
+    tail = 0.0
+    for value in torch.unique(x64).flip(0).tolist():
+        group = x64 == value
+        mass = e[group].sum().item()
+        if tail + mass <= budget:
+            keep |= group
+            tail += mass
+            continue
+        each = e[group][0].item()
+        n = int((budget.item() - tail) // each)
+        if tail == 0.0:
+            n = max(n, 1)
+        idx = group.nonzero().flatten()[:n]
+        keep[idx] = True
+        break
+    return torch.where(keep, e, torch.zeros_like(e))
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('V,top_p,spread', [(4096, 0.9, 3.0), (8192, 0.5, 1.0), (1000, 0.97, 6.0), (4096, 1.0, 2.0)])
+def test_sampler_draws_the_inverse_cdf_token_of_the_reference_nucleus(dtype, V, top_p, spread):
+    """V <= 8192: the kernel's sampling order is the index order, so the token for a given uniform is known exactly."""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(V + int(100 * top_p))
+    row = (torch.randn(V, generator=g) * spread).to(dtype)
+    B = 1024
+    logits = row.to(dev)[None].repeat(B, 1).contiguous()
+    uniforms = torch.rand(B, generator=g).to(dev)
+    ids, _, _ = _run_sampler(logits, uniforms, top_p=top_p, end_token=-1)
+    got = ids[:, 1].cpu()
+    w = _nucleus_weights(row.double(), top_p)
+    # the reference's own rule (sort, softmax, cumsum > top_p masked, first kept) keeps the same set up to boundary ties
+    sorted_x, order = row.float().sort(descending=True)
+    probs = sorted_x.softmax(-1)
+    tail = probs.cumsum(-1) > top_p
+    tail[0] = False
+    ref_keep = torch.zeros(V, dtype=torch.bool)
+    ref_keep[order[~tail]] = True
+    boundary = row.float()[w > 0].min()
+    differs = (ref_keep != (w > 0))
+    assert (row.float()[differs] == boundary).all() and differs.sum() <= 2 + (row.float() == boundary).sum()
+    cdf = w.cumsum(0)
+    want = torch.searchsorted(cdf, uniforms.cpu().double() * cdf[-1], right=True).clamp_(max=V - 1)
+    mismatch = (got != want)
+    assert mismatch.float().mean() <= 0.005, (got[mismatch][:8], want[mismatch][:8])
+    assert (w[got] > 0).all()                      # never a token outside the nucleus
+
+
+def test_sampler_full_vocab_frequencies():
+    """V = 32768 (four register chunks per thread): empirical frequencies of the likeliest tokens vs the nucleus."""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(9)
+    V, B = 32768, 8192
+    row = (torch.randn(V, generator=g) * 2.5).to(torch.float16)
+    logits = row.to(dev)[None].repeat(B, 1).contiguous()
+    uniforms = torch.rand(B, generator=g).to(dev)
+    ids, _, _ = _run_sampler(logits, uniforms, top_p=0.9, end_token=-1)
+    got = ids[:, 1].cpu()
+    w = _nucleus_weights(row.double(), 0.9)
+    p = w / w.sum()
+    assert (w[got] > 0).all()
+    counts = torch.bincount(got, minlength=V).double()
+    top = p.topk(12).indices
+    sigma = (B * p[top] * (1 - p[top])).sqrt()
+    assert ((counts[top] - B * p[top]).abs() <= 5 * sigma + 1).all(), (counts[top], B * p[top])
+    # inverse CDF from evenly spread uniforms covers the nucleus evenly: total variation stays small
+    assert 0.5 * (counts / B - p).abs().sum() <= 0.5
+
+
+def test_sampler_penalty_temperature_and_bookkeeping():
+    dev = torch.device('cuda')
+    V = 32768
+    logits = torch.full((4, V), -8.0, dtype=torch.float16, device=dev)
+    logits[:, 100], logits[:, 200], logits[:, 300] = 5.0, 4.5, -7.0
+    ids = torch.zeros(4, 8, dtype=torch.long, device=dev)
+    ids[0, :3] = torch.tensor([1, 100, 7])            # row 0 has generated token 100 -> 5.0 / 1.2 < 4.5
+    ids[1, :3] = torch.tensor([1, 300, 7])            # negative logits are multiplied: -7 * 1.2, irrelevant for the argmax
+    ids[2, :3] = torch.tensor([1, 100, 7])            # dead row: nothing written
+    ids[3, :3] = torch.tensor([1, 9, 200])            # row 3 draws 100 = its end token
+    alive = torch.tensor([True, True, False, True], device=dev)
+    uniforms = torch.full((4,), 0.3, device=dev)
+    out, alive, finished = _run_sampler(logits, uniforms, ids=ids, column=3, alive=alive, penalty=1.2, top_p=0.05,
+                                        end_token=100)
+    # row 3: token 200 was generated -> 4.5 / 1.2 = 3.75, so 100 wins and ends the sample
+    assert out[:, 3].tolist() == [200, 100, 0, 100]
+    assert alive.tolist() == [True, False, False, False] and finished == 2
+    # temperature: dividing by 0.01 makes the distribution a point mass even with top_p = 1
+    out, _, _ = _run_sampler(logits, torch.rand(4, device=dev), column=1, temperature=0.01, top_p=1.0, end_token=-1)
+    assert out[:, 1].tolist() == [100] * 4
