@@ -238,6 +238,11 @@ SVAE_API int svae_decode_attn(const void* q, const void* k, const void* v, const
                      const int32_t* position, int32_t B, int32_t H, int32_t head_dim, int32_t window, int32_t block,
                      int32_t table_rows, int64_t in_stride, int32_t dtype, float scale, void* stream);
 
+/* Decoding step glue: x (fp32 residual stream, updated in place) += h, then y = LayerNorm(x) with the arithmetic of
+ * svae_layernorm_fwd (reference core/transformer_layer.py:35-61: `x = x + h` followed by the next sub-layer's norm). */
+SVAE_API int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
+                            int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, void* stream);
+
 /* One-launch restatement of GenerationState.process_logits with its default settings (reference
  * core/generation.py:40-72): repetition penalty over the last `penalty_window` generated tokens, temperature, nucleus
  * filtering (largest set of most likely tokens with mass <= top_p, never empty), one categorical draw per row by

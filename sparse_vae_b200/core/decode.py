@@ -122,6 +122,20 @@ class GraphedDecoder:
                                        N.current_stream(qkv.device)), 'svae_decode_attn')
         return F.linear(out, w.wo, w.bo)
 
+    def _add_norm(self, x: Tensor, h: Tensor, norm) -> Tensor:
+        """x += h (in place, fp32) and LayerNorm(x) in the activation dtype: one launch for the residual update and
+        the next sub-layer's norm (reference core/transformer_layer.py:35-61)."""
+        n = x.shape[-1]
+        if not (norm.elementwise_affine and norm.weight.dtype == torch.float32 and h.dtype == self.dtype
+                and h.is_contiguous() and N.lib.svae_layernorm_supported(n)):
+            x += h
+            return norm(x)
+        y = torch.empty_like(h)
+        N.check(N.lib.svae_residual_layernorm(x.data_ptr(), h.data_ptr(), N.svae_dtype(h.dtype), norm.weight.data_ptr(),
+                                              N.ptr(norm.bias), x.numel() // n, n, float(norm.eps), y.data_ptr(),
+                                              N.svae_dtype(h.dtype), N.current_stream(x.device)), 'svae_residual_layernorm')
+        return y
+
     def _process_logits(self, logits: Tensor) -> Tensor:
         """core/generation.py:40-72 with the live batch fixed: same ops on the same values, static shapes."""
         st = self.state
@@ -157,11 +171,16 @@ class GraphedDecoder:
         model = self.model
         B = self.ids.shape[0]
         prev = self.ids.gather(1, (self.column - 1).expand(B, 1))
-        x = model.input_layer(prev)                                         # [B, 1, D], fp32 residual stream
-        for layer, w in zip(model.decoder_layers, self.layers):
-            x = x + self._attend(layer.attention, w, layer.attn_layer_norm(x))
-            h = F.linear(F.gelu(F.linear(layer.ffn_layer_norm(x), w.w1, w.b1)), w.w2)
-            x = x + layer.dropout(h)
+        x = model.input_layer(prev).float().contiguous()                    # [B, 1, D] fp32 residual stream (own buffer)
+        y = model.decoder_layers[0].attn_layer_norm(x)
+        last = len(self.layers) - 1
+        for i, (layer, w) in enumerate(zip(model.decoder_layers, self.layers)):
+            y = self._add_norm(x, self._attend(layer.attention, w, y), layer.ffn_layer_norm)
+            h = layer.dropout(F.linear(F.gelu(F.linear(y, w.w1, w.b1)), w.w2))
+            if i < last:
+                y = self._add_norm(x, h, model.decoder_layers[i + 1].attn_layer_norm)
+            else:
+                x = x + h
         head = model.output_layer
         h = head[2](F.gelu(F.linear(x.squeeze(1).to(self.dtype), self.head_w0, self.head_b0)))
         logits = F.linear(h, self.head_w3, self.head_b3)

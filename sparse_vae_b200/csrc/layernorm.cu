@@ -103,6 +103,50 @@ layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, 
   }
 }
 
+// Token-by-token decoding (core/decode.py): the residual stream update and the next LayerNorm in one pass.
+// x (fp32, in place) += h; y = LayerNorm(x).  Same arithmetic as the separate `x + h` (fp32 add of the promoted
+// 16-bit branch output) followed by layernorm_fwd_kernel; no statistics are kept (inference only).
+template <typename TH, typename TY, int VPT>
+__global__ void __launch_bounds__(kLnThreads)
+residual_layernorm_kernel(float* __restrict__ x, const TH* __restrict__ h, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, TY* __restrict__ y, int64_t rows, float eps) {
+  constexpr int N = 128 * VPT;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kLnWarps;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float v[VPT][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float hv[4];
+      Vec4<float>::load(x + r * N + (i * 32 + lane) * 4, v[i]);
+      Vec4<TH>::load(h + r * N + (i * 32 + lane) * 4, hv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i][e] += hv[e];
+      Vec4<float>::store(x + r * N + (i * 32 + lane) * 4, v[i]);
+      s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+    const float mean = warp_sum(s) * (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / N) + eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      float g[4], bt[4], o[4];
+      Vec4<float>::load(gamma + (i * 32 + lane) * 4, g);
+      if (beta) Vec4<float>::load(beta + (i * 32 + lane) * 4, bt);
+      else bt[0] = bt[1] = bt[2] = bt[3] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, g[e], bt[e]);
+      Vec4<TY>::store(y + r * N + (i * 32 + lane) * 4, o);
+    }
+  }
+}
+
 // dx = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) ; partial[block] = {sum dy*xhat, sum dy}
 template <typename TX, typename TY, int VPT>
 __global__ void __launch_bounds__(kLnThreads)
@@ -222,6 +266,18 @@ static int launch_bwd(int vpt, const void* dy, const void* x, const float* gamma
   return SVAE_OK;
 }
 
+template <typename TH, typename TY>
+static int launch_residual(int vpt, float* x, const void* h, const float* gamma, const float* beta, void* y, int64_t rows,
+                           float eps, cudaStream_t st) {
+  const int grid = ln_grid(rows);
+#define SVAE_LN_RES(V)                                                                                         \
+  case V: residual_layernorm_kernel<TH, TY, V><<<grid, kLnThreads, 0, st>>>(x, (const TH*)h, gamma, beta, (TY*)y, rows, eps); break
+  switch (vpt) { SVAE_LN_RES(1); SVAE_LN_RES(2); SVAE_LN_RES(4); SVAE_LN_RES(8); default: return SVAE_ERR_UNSUPPORTED; }
+#undef SVAE_LN_RES
+  SVAE_CUDA_CHECK(cudaGetLastError());
+  return SVAE_OK;
+}
+
 static bool ln_shape_ok(int32_t n) { return n == 128 || n == 256 || n == 512 || n == 1024; }
 
 }  // namespace svae
@@ -274,4 +330,18 @@ extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x
     SVAE_CUDA_CHECK(cudaGetLastError());
   }
   return SVAE_OK;
+}
+
+extern "C" int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
+                                       int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(x && h && gamma && y && rows >= 0, SVAE_ERR_INVALID, "svae_residual_layernorm: null argument");
+  SVAE_REQUIRE(ln_shape_ok(n), SVAE_ERR_UNSUPPORTED, "svae_residual_layernorm: width %d not in {128, 256, 512, 1024}", n);
+  SVAE_REQUIRE(h_dtype == y_dtype && (h_dtype == SVAE_DTYPE_F16 || h_dtype == SVAE_DTYPE_BF16 || h_dtype == SVAE_DTYPE_F32),
+               SVAE_ERR_UNSUPPORTED, "svae_residual_layernorm: branch and output must share one dtype (%d, %d)", h_dtype, y_dtype);
+  if (rows == 0) return SVAE_OK;
+  ScopedKernelTimer timer("residual_layernorm", st);
+  if (h_dtype == SVAE_DTYPE_F16) return launch_residual<__half, __half>(n / 128, x, h, gamma, beta, y, rows, eps, st);
+  if (h_dtype == SVAE_DTYPE_BF16) return launch_residual<__nv_bfloat16, __nv_bfloat16>(n / 128, x, h, gamma, beta, y, rows, eps, st);
+  return launch_residual<float, float>(n / 128, x, h, gamma, beta, y, rows, eps, st);
 }

@@ -284,3 +284,27 @@ def test_sampler_penalty_temperature_and_bookkeeping():
     # temperature: dividing by 0.01 makes the distribution a point mass even with top_p = 1
     out, _, _ = _run_sampler(logits, torch.rand(4, device=dev), column=1, temperature=0.01, top_p=1.0, end_token=-1)
     assert out[:, 1].tolist() == [100] * 4
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('rows,n', [(1, 128), (256, 512), (37, 1024)])
+def test_residual_layernorm_equals_add_then_layernorm(dtype, rows, n):
+    """x += h; y = LN(x): bit-identical to the separate fp32 add and the LayerNorm kernel it replaces while decoding."""
+    from sparse_vae_b200 import _native as N
+    from sparse_vae_b200.core.layer_norm import LayerNorm
+    dev = torch.device('cuda')
+    torch.manual_seed(rows + n)
+    norm = LayerNorm(n).to(dev)
+    with torch.no_grad():
+        norm.weight.normal_(1, 0.2)
+        norm.bias.normal_(0, 0.2)
+    x = torch.randn(rows, 1, n, device=dev) * 2
+    h = torch.randn(rows, 1, n, device=dev).to(dtype)
+    want_x = x + h
+    with torch.no_grad(), torch.autocast('cuda', dtype=dtype, enabled=dtype != torch.float32):
+        want_y = norm(want_x)
+    y = torch.empty_like(h)
+    N.check(N.lib.svae_residual_layernorm(x.data_ptr(), h.data_ptr(), N.svae_dtype(dtype), norm.weight.data_ptr(),
+                                          norm.bias.data_ptr(), rows, n, norm.eps, y.data_ptr(), N.svae_dtype(dtype),
+                                          N.current_stream(dev)), 'svae_residual_layernorm')
+    assert torch.equal(x, want_x) and want_y.dtype == dtype and torch.equal(y, want_y)
