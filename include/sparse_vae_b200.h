@@ -238,6 +238,10 @@ SVAE_API int svae_decode_attn(const void* q, const void* k, const void* v, const
                      const int32_t* position, int32_t B, int32_t H, int32_t head_dim, int32_t window, int32_t block,
                      int32_t table_rows, int64_t in_stride, int32_t dtype, float scale, void* stream);
 
+/* Residual-stream update under autocast (reference core/transformer_layer.py:41,49,61 `x = x + h`): out = x + h with
+ * x, out fp32 and h 16-bit, numel % 8 == 0, 16-byte aligned; out == x is allowed. */
+SVAE_API int svae_residual_add(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, void* stream);
+
 /* Decoding step glue: x (fp32 residual stream, updated in place) += h, then y = LayerNorm(x) with the arithmetic of
  * svae_layernorm_fwd (reference core/transformer_layer.py:35-61: `x = x + h` followed by the next sub-layer's norm). */
 SVAE_API int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,

@@ -37,7 +37,7 @@ EXPORTS = (
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
     'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
-    'svae_residual_layernorm',
+    'svae_residual_layernorm', 'svae_residual_add',
 )
 
 
@@ -127,6 +127,8 @@ def _load() -> C.CDLL:
     lib.svae_decode_attn_supported.argtypes = [i32, i32, i32]
     lib.svae_decode_attn.restype = C.c_int
     lib.svae_decode_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i32, C.c_float, vp]
+    lib.svae_residual_add.restype = C.c_int
+    lib.svae_residual_add.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.svae_residual_layernorm.restype = C.c_int
     lib.svae_residual_layernorm.argtypes = [vp, vp, i32, vp, vp, i64, i32, C.c_float, vp, i32, vp]
     lib.svae_sample_top_p_supported.restype = C.c_int

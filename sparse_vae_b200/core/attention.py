@@ -21,6 +21,7 @@ from .. import _native as N
 from .layer_norm import LayerNorm
 from .linear import Linear
 from .padded_tensor import PaddedTensor, split_padding
+from .residual import residual_add
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
 
@@ -248,16 +249,16 @@ class TransformerLayer(nn.Module):
         padding = x_pad if padding is None else padding
         h = self.attn_layer_norm(x)
         h = self.attention(h, h, h, padding=padding)
-        x = x + h if x.shape == h.shape else h              # learned queries change the length: no residual
+        x = residual_add(x, h) if x.shape == h.shape else h  # learned queries change the length: no residual
 
         if self.cross_attention and context is not None:
             context, c_pad = split_padding(context)
             context_padding = c_pad if context_padding is None else context_padding
             h = self.cross_attention(self.cross_attn_layer_norm(x), *(self.context_layer_norm(context),) * 2,
                                      padding=context_padding)
-            x = x + h
+            x = residual_add(x, h)
 
-        return x + self.dropout(self.ffn(self.ffn_layer_norm(x)))
+        return residual_add(x, self.dropout(self.ffn(self.ffn_layer_norm(x))))
 
 
 class Perceiver(nn.Module):

@@ -19,7 +19,7 @@ BUILD = HERE / 'build'
 LIB = HERE / 'libsvae_b200.so'
 SOURCES = ['abi.cu', 'bottleneck.cu', 'attn_exact.cu', 'attn_fwd_sm100.cu', 'attn_fwd_persist_sm100.cu', 'attn_bwd_sm100.cu', 'attn_dispatch.cu',
            'debug_mma_bench.cu', 'debug_pipe_bench.cu', 'optim.cu', 'layernorm.cu', 'vocab_ce.cu', 'rotary.cu', 'colsum.cu',
-           'decode_attn.cu', 'sampling.cu']
+           'decode_attn.cu', 'sampling.cu', 'residual.cu']
 HEADERS = ['common.cuh', 'sm100_ptx.cuh', 'attn_sm100.cuh', '../../include/sparse_vae_b200.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

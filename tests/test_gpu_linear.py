@@ -56,3 +56,27 @@ def test_linear_plain_paths_are_nn_linear():
     lin = lin.cuda()
     xc = torch.randn(2000, 64, device='cuda', requires_grad=True)
     torch.testing.assert_close(lin(xc), torch.nn.functional.linear(xc, lin.weight, lin.bias))     # no autocast
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('shape', [(16, 4096, 512), (3, 1, 8), (2, 37, 256)])
+def test_residual_add_equals_aten_mixed_add(dtype, shape):
+    """fp32 stream + 16-bit branch: values and both gradients bit-identical to `x + h`."""
+    from sparse_vae_b200.core.residual import _ResidualAddFn, residual_add
+    dev = torch.device('cuda')
+    torch.manual_seed(sum(shape))
+    x = torch.randn(*shape, device=dev, requires_grad=True)
+    h = torch.randn(*shape, device=dev).to(dtype).requires_grad_()
+    g = torch.randn(*shape, device=dev)
+    out = residual_add(x, h)
+    assert isinstance(out.grad_fn, _ResidualAddFn._backward_cls)
+    out.backward(g)
+    got = (out.detach().clone(), x.grad.clone(), h.grad.clone())
+    x.grad = h.grad = None
+    ref = x + h
+    ref.backward(g)
+    assert torch.equal(got[0], ref) and torch.equal(got[1], x.grad) and torch.equal(got[2], h.grad)
+    assert got[2].dtype == dtype
+    # shapes the kernel does not take fall back to the plain expression
+    y = residual_add(x[..., :7], h[..., :7])
+    assert torch.equal(y, x[..., :7] + h[..., :7])
