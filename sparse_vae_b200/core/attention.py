@@ -15,6 +15,7 @@ from contextlib import contextmanager
 from typing import Optional, Set, Tuple, Union
 
 import torch
+import torch.nn.functional as F
 from torch import nn, Tensor
 
 from .. import _native as N
@@ -150,6 +151,13 @@ class Attention(nn.Module):
         if sparse and self.key_cache is None:
             kpm = padding * -1e7 if padding is not None else None
             out = sparse(q, k, v, key_padding_mask=kpm)                                 # [B, H, L, Dh] over [B, L, H, Dh]
+        elif (N.FUSED_EXTRAS and q.is_cuda and self.key_cache is None and q.ndim == 4
+              and (padding is None or (padding.ndim == 2 and not self.causal))):
+            # Dense attention of the Perceiver encoder (64 learned queries over the whole sequence) and of non-sparse
+            # decoders: same arithmetic -- softmax(q k^T / sqrt(d) - 1e7 * mask) v -- through the library's fused
+            # kernel, which reads the strided head views directly (the explicit form copies k^T and v per call).
+            bias = None if padding is None else (padding[:, None, None, :] * -1e7).to(q.dtype)    # autocast casts it along
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, is_causal=self.causal and bias is None)
         else:
             scores = q @ k.transpose(-1, -2) * k.shape[-1] ** -0.5
             mask = padding[..., None, None, :] if padding is not None and padding.ndim >= 2 else padding
