@@ -166,6 +166,10 @@ SVAE_API int64_t svae_multi_tensor_chunks(int32_t n, const int64_t* numel);
  * all-reduce buckets of the data-parallel trainer (and folds the 1/world_size averaging in). */
 SVAE_API int svae_multi_tensor_scale_copy(int32_t n, void* const* dst, void* const* src, const int64_t* numel, float scale,
                                  void* stream);
+/* dst[i] = (dst_dtype) src[i] over two equally shaped lists (src fp32): the autocast-dtype copies of the projection
+ * weights for one training step, in a handful of launches.  dst_dtype: SVAE_DTYPE_BF16 or SVAE_DTYPE_F16. */
+SVAE_API int svae_multi_tensor_cast(int32_t n, void* const* dst, void* const* src, const int64_t* numel, int32_t dst_dtype,
+                           void* stream);
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) as called by LanguageModel.on_after_backward
  * (sparse_vae/core/language_model.py:120-122): norm_coef[0] = || all grads ||_2, norm_coef[1] =
  * min(1, max_norm / (norm + 1e-6)), every gradient multiplied in place by norm_coef[1].  Deterministic

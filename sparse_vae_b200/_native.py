@@ -37,7 +37,7 @@ EXPORTS = (
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
     'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
-    'svae_residual_layernorm', 'svae_residual_add',
+    'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast',
 )
 
 
@@ -101,6 +101,8 @@ def _load() -> C.CDLL:
     lib.svae_multi_tensor_chunks.argtypes = [i32, vp]
     lib.svae_multi_tensor_scale_copy.restype = C.c_int
     lib.svae_multi_tensor_scale_copy.argtypes = [i32, vp, vp, vp, C.c_float, vp]
+    lib.svae_multi_tensor_cast.restype = C.c_int
+    lib.svae_multi_tensor_cast.argtypes = [i32, vp, vp, vp, i32, vp]
     lib.svae_clip_grad_norm.restype = C.c_int
     lib.svae_clip_grad_norm.argtypes = [i32, vp, vp, C.c_float, vp, i64, vp, vp]
     lib.svae_radam_step.restype = C.c_int

@@ -231,7 +231,7 @@ class TransformerLayer(nn.Module):
                  sparse_self_attention: Union[bool, int] = False, learned_queries: int = None):
         super().__init__()
         self.attention = Attention(d_model, num_heads, causal, learned_queries=learned_queries, sparse=sparse_self_attention)
-        self.ffn = nn.Sequential(Linear(d_model, d_model * 4), nn.GELU(), nn.Linear(d_model * 4, d_model, bias=False))
+        self.ffn = nn.Sequential(Linear(d_model, d_model * 4), nn.GELU(), Linear(d_model * 4, d_model, bias=False))
         self.dropout = nn.Dropout(p=0.1)
         self.attn_layer_norm = LayerNorm(d_model)
         self.ffn_layer_norm = LayerNorm(d_model)

@@ -5,15 +5,25 @@ Forward is the library GEMM the reference uses (`F.linear` on the autocast-dtype
 the two library GEMMs, with the weight gradient accumulated and written in fp32 (the reference rounds it to the
 autocast dtype before casting back), and the bias gradient from the two-stage column-sum kernel `svae_colsum`
 (csrc/colsum.cu) instead of ATen's generic reduction (~1.6 TB/s at [65536, 512]).  Outside autocast, on the CPU, for
-small inputs or without a bias it is exactly `nn.Linear`.
+small inputs it is exactly `nn.Linear`.
+
+`WeightShadows` removes the per-weight autocast casts: under autocast every `nn.Linear` casts its fp32 weight (and
+bias) to the 16-bit dtype once per step -- ~150 launches of a few microseconds each for this model.  The shadow set
+holds one flat 16-bit buffer with a view per `Linear` parameter and refreshes ALL of them with a handful of
+multi-tensor launches (`svae_multi_tensor_cast`, same rounding as `.to(dtype)`) when a step begins; while the
+step's forward runs, `Linear` reads those views instead of casting.
 """
 from __future__ import annotations
+
+from contextlib import contextmanager
+from typing import List, Optional
 
 import torch
 import torch.nn.functional as F
 from torch import nn, Tensor
 
 from .. import _native as N
+from ..fused_optim import _PtrList
 
 _MIN_ROWS = 1024
 
@@ -31,15 +41,23 @@ def colsum(x2d: Tensor) -> Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x: Tensor, weight: Tensor, bias: Tensor, dtype: torch.dtype):
-        x16, w16 = x.to(dtype), weight.to(dtype)
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], dtype: torch.dtype, w16: Optional[Tensor],
+                b16: Optional[Tensor], shadows: Optional['WeightShadows']):
+        x16 = x.to(dtype)
+        if w16 is None:
+            w16 = weight.to(dtype)
+            b16 = bias.to(dtype) if bias is not None else None
         ctx.save_for_backward(x16, w16)
-        ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype)
-        return F.linear(x16, w16, bias.to(dtype))
+        ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        ctx.shadows, ctx.epoch = shadows, (shadows.epoch if shadows is not None else 0)
+        return F.linear(x16, w16, b16)
 
     @staticmethod
     def backward(ctx, g: Tensor):
         x16, w16 = ctx.saved_tensors
+        if ctx.shadows is not None and ctx.shadows.epoch != ctx.epoch:
+            raise RuntimeError("a weight needed for this backward pass was modified (optimizer step?) after the forward "
+                               "pass that used its 16-bit shadow copy")
         xd, wd, bd = ctx.in_dtypes
         n_out, n_in = w16.shape
         g2 = g.reshape(-1, n_out)
@@ -50,17 +68,100 @@ class _LinearFn(torch.autograd.Function):
             dx = torch.mm(g2, w16).view(x16.shape).to(xd)
         if ctx.needs_input_grad[1]:
             dw = torch.mm(g2.t(), x16.reshape(-1, n_in), out_dtype=torch.float32).to(wd)
-        if ctx.needs_input_grad[2]:
+        if bd is not None and ctx.needs_input_grad[2]:
             db = colsum(g2).to(bd)
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None, None
 
 
 class Linear(nn.Linear):
+    _shadow = None          # (WeightShadows, weight view, bias view | None), set by WeightShadows
+
     def forward(self, x: Tensor) -> Tensor:
-        if (N.FUSED_EXTRAS and x.is_cuda and self.bias is not None and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
+        if (N.FUSED_EXTRAS and x.is_cuda and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
                 and self.out_features % 8 == 0 and x.numel() >= _MIN_ROWS * self.in_features
                 and (x.requires_grad or self.weight.requires_grad)):
             dtype = torch.get_autocast_dtype('cuda')
             if dtype in (torch.bfloat16, torch.float16):
-                return _LinearFn.apply(x, self.weight, self.bias, dtype)
+                sh = self._shadow
+                if sh is not None and sh[0] is WeightShadows.ACTIVE and sh[1].dtype == dtype:
+                    return _LinearFn.apply(x, self.weight, self.bias, dtype, sh[1], sh[2], sh[0])
+                return _LinearFn.apply(x, self.weight, self.bias, dtype, None, None, None)
         return F.linear(x, self.weight, self.bias)
+
+
+class WeightShadows:
+    """16-bit copies of the parameters of every `Linear` below `root`, refreshed together once per training step.
+
+        with shadows.step():            # refresh (a few launches), then let the Linear layers use the copies
+            loss = forward(...)
+        loss.backward()                 # the saved views stay valid until the next refresh changes their values
+
+    The copies are only read while `step()` is open and they are rebuilt from the fp32 parameters every time it is
+    entered, so any update of the parameters between steps (optimizers, `load_state_dict`, `.data` writes) is picked
+    up.  A backward pass that runs after the parameters changed AND the copies were refreshed raises, like autograd
+    does for a modified fp32 weight."""
+
+    ACTIVE: Optional['WeightShadows'] = None
+    ENABLED = True              # tests switch the mechanism off to compare against the per-weight casts
+
+    def __init__(self, root: nn.Module):
+        self.root = root
+        self.epoch = 0
+        self._params: List[Tensor] = []
+        self._views: List[Tensor] = []
+        self._flat = None
+        self._key = None
+        self._versions = None
+        self._dst, self._src = _PtrList(), _PtrList()
+
+    def _collect(self, dtype: torch.dtype):
+        mods = [m for m in self.root.modules() if isinstance(m, Linear) and m.weight.is_cuda
+                and m.weight.dtype == torch.float32 and m.weight.is_contiguous()]
+        params, index = [], {}
+        for m in mods:
+            for t in (m.weight, m.bias):
+                if t is not None and id(t) not in index and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+                    index[id(t)] = len(params)
+                    params.append(t)
+        offsets, total = [], 0
+        for t in params:
+            offsets.append(total)
+            total += (t.numel() + 7) // 8 * 8                   # 16-byte aligned views
+        dev = params[0].device if params else torch.device('cuda')
+        self._flat = torch.empty(max(total, 8), dtype=dtype, device=dev)
+        self._params = params
+        self._views = [self._flat[o:o + t.numel()].view(t.shape) for o, t in zip(offsets, params)]
+        for m in self.root.modules():
+            if isinstance(m, Linear):
+                m._shadow = None
+        for m in mods:
+            if id(m.weight) not in index or (m.bias is not None and id(m.bias) not in index):
+                continue
+            m._shadow = (self, self._views[index[id(m.weight)]],
+                         self._views[index[id(m.bias)]] if m.bias is not None else None)
+
+    def refresh(self):
+        dtype = torch.get_autocast_dtype('cuda')
+        key = (dtype,) + tuple((id(m), m.weight.data_ptr(), None if m.bias is None else m.bias.data_ptr())
+                               for m in self.root.modules() if isinstance(m, Linear))
+        if key != self._key:
+            self._collect(dtype)
+            self._key = key
+        if not self._params:
+            return
+        d, s = self._dst.update(self._views), self._src.update(self._params)
+        N.check(N.lib.svae_multi_tensor_cast(d.n, d.ptrs, s.ptrs, s.numel, N.svae_dtype(dtype),
+                                             N.current_stream(self._params[0].device)), 'svae_multi_tensor_cast')
+        versions = sum(t._version for t in self._params)
+        if versions != self._versions:
+            self._versions = versions
+            self.epoch += 1
+
+    @contextmanager
+    def step(self):
+        self.refresh()
+        previous, WeightShadows.ACTIVE = WeightShadows.ACTIVE, self
+        try:
+            yield self
+        finally:
+            WeightShadows.ACTIVE = previous

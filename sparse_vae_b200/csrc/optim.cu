@@ -167,6 +167,30 @@ __global__ void __launch_bounds__(kMtThreads) scale_copy_kernel(const __grid_con
   }
 }
 
+// dst[i] = T(src[i]) over every tensor of the list: the autocast-dtype copies of all projection weights in a few launches
+// (core/weight_shadows.py) instead of one ATen cast launch per weight and per step.  Same rounding as `.to(dtype)`.
+template <typename T>
+__global__ void __launch_bounds__(kMtThreads) cast_copy_kernel(const __grid_constant__ MtTable<2> t) {
+  const int ti = t.block_tensor[blockIdx.x];
+  const int64_t base = (int64_t)t.block_chunk[blockIdx.x] * kMtChunk;
+  const int64_t n = t.numel[ti];
+  T* d = reinterpret_cast<T*>(t.ptr[0][ti]) + base;
+  const float* s = reinterpret_cast<const float*>(t.ptr[1][ti]) + base;
+  const int cnt = (int)((n - base) < kMtChunk ? (n - base) : kMtChunk);
+  if ((reinterpret_cast<uintptr_t>(s) & 15) == 0 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+    const int n4 = cnt >> 2;
+    for (int i = threadIdx.x; i < n4; i += kMtThreads) {
+      const float4 x = ld4(s + 4 * i);
+      struct alignas(8) Out4 { T v[4]; } o;
+      o.v[0] = from_f32<T>(x.x); o.v[1] = from_f32<T>(x.y); o.v[2] = from_f32<T>(x.z); o.v[3] = from_f32<T>(x.w);
+      *reinterpret_cast<Out4*>(d + 4 * i) = o;
+    }
+    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += kMtThreads) d[i] = from_f32<T>(s[i]);
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += kMtThreads) d[i] = from_f32<T>(s[i]);
+  }
+}
+
 // Walks the tensor list, filling launch tables; calls launch(table, blocks, first_block_index) whenever one is full.
 template <int NPTR, typename Launch>
 static int for_each_table(int n, void* const* const* lists, const int64_t* numel, Launch&& launch) {
@@ -217,6 +241,22 @@ extern "C" int svae_multi_tensor_scale_copy(int32_t n, void* const* dst, void* c
   ScopedKernelTimer timer("grad_gather", st);
   return for_each_table<2>(n, lists, numel, [&](const MtTable<2>& t, int nb, int) -> int {
     scale_copy_kernel<<<nb, kMtThreads, 0, st>>>(t, scale);
+    SVAE_CUDA_CHECK(cudaGetLastError());
+    return SVAE_OK;
+  });
+}
+
+extern "C" int svae_multi_tensor_cast(int32_t n, void* const* dst, void* const* src, const int64_t* numel, int32_t dst_dtype,
+                                     void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(n >= 0 && dst && src && numel, SVAE_ERR_INVALID, "svae_multi_tensor_cast: null argument");
+  SVAE_REQUIRE(dst_dtype == SVAE_DTYPE_BF16 || dst_dtype == SVAE_DTYPE_F16, SVAE_ERR_UNSUPPORTED,
+               "svae_multi_tensor_cast: destination dtype %d (bf16 / f16 only)", dst_dtype);
+  void* const* lists[2] = {dst, src};
+  ScopedKernelTimer timer("weight_cast", st);
+  return for_each_table<2>(n, lists, numel, [&](const MtTable<2>& t, int nb, int) -> int {
+    if (dst_dtype == SVAE_DTYPE_BF16) cast_copy_kernel<__nv_bfloat16><<<nb, kMtThreads, 0, st>>>(t);
+    else cast_copy_kernel<__half><<<nb, kMtThreads, 0, st>>>(t);
     SVAE_CUDA_CHECK(cudaGetLastError());
     return SVAE_OK;
   });

@@ -81,6 +81,8 @@ class FusedRAdamStep:
         N.check(N.lib.svae_radam_step(p.n, p.ptrs, g.ptrs, m.ptrs, v.ptrs, p.numel, float(lr), float(beta1), float(beta2),
                                       float(eps), float(weight_decay), int(step), N.current_stream(dev)),
                 'svae_radam_step')
+        # the kernel wrote through raw pointers: tell autograd (and anything keyed on tensor versions) about it
+        torch.autograd.graph.increment_version(params)
 
 
 class FusedScaleCopy:

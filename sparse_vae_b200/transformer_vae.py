@@ -20,6 +20,7 @@ from . import _native as N
 from .core import decode, fused_ce
 from .core.generation import GenerationState
 from .core.lightning_shim import DictConfig
+from .core.linear import WeightShadows
 from .core.math_utils import marginal_kl
 from .core.padded_tensor import split_padding
 from .core.transformer_language_model import TransformerHparams, TransformerLanguageModel
@@ -72,6 +73,18 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         self.z_projections = nn.ModuleList(nn.Linear(hp.latent_depth, hp.d_model) for _ in range(hp.num_layers))
 
     def training_step(self, batch: Dict[str, Tensor], batch_index: int, stage: str = 'train'):
+        if (N.FUSED_EXTRAS and WeightShadows.ENABLED and self.device.type == 'cuda' and torch.is_autocast_enabled('cuda')
+                and torch.is_grad_enabled()
+                and torch.get_autocast_dtype('cuda') in (torch.bfloat16, torch.float16)):
+            # one multi-tensor launch refreshes the 16-bit copies of all projection weights for this step
+            shadows = self.__dict__.get('_weight_shadows')
+            if shadows is None:
+                shadows = self.__dict__['_weight_shadows'] = WeightShadows(self)
+            with shadows.step():
+                return self._training_step(batch, batch_index, stage)
+        return self._training_step(batch, batch_index, stage)
+
+    def _training_step(self, batch: Dict[str, Tensor], batch_index: int, stage: str = 'train'):
         tokens, padding = split_padding(batch['token_ids'])
         original = tokens.long()
         if padding is None:

@@ -80,3 +80,66 @@ def test_residual_add_equals_aten_mixed_add(dtype, shape):
     # shapes the kernel does not take fall back to the plain expression
     y = residual_add(x[..., :7], h[..., :7])
     assert torch.equal(y, x[..., :7] + h[..., :7])
+
+
+def test_weight_shadows_give_identical_training_steps():
+    """One multi-tensor cast per step instead of one autocast cast per weight: same rounding of the same fp32 weights,
+    so the first loss is bit-identical; gradients (and the losses after an update) agree up to the run-to-run noise
+    of the backward pass (fp32 atomics for the global key block, whose results are then rounded to bf16: single
+    elements move by a bf16 ulp between two runs of the SAME configuration)."""
+    import sparse_vae_b200 as sv
+    from sparse_vae_b200.core.lightning_shim import to_attrdict
+    from sparse_vae_b200.core.linear import WeightShadows
+    from sparse_vae_b200.synthetic import synthetic_tokens, to_device
+    dev = torch.device('cuda')
+
+    def run(enabled):
+        WeightShadows.ENABLED = enabled
+        try:
+            torch.manual_seed(3)
+            model = sv.TransformerVAE(to_attrdict(sv.TransformerVAEHparams(d_model=256, num_layers=4, latent_depth=16))).to(dev).eval()
+            model.initialize_weights()
+            (opt,), _ = model.configure_optimizers(tokens_per_batch=4 * 2048)
+            batch = to_device(synthetic_tokens(4, 2048, seed=1), dev)
+            losses, first_grads = [], None
+            for step in range(3):
+                for p in model.parameters():
+                    p.grad = None
+                torch.manual_seed(100 + step)
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    loss = model.training_step(batch, step)['loss']
+                loss.backward()
+                losses.append(loss.detach().clone())
+                if step == 0:                     # before any update: only the atomics' summation order differs
+                    first_grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+                opt.step()
+            used = model.__dict__.get('_weight_shadows')
+            return losses, first_grads, used
+        finally:
+            WeightShadows.ENABLED = True
+
+    la, ga, used = run(True)
+    lb, gb, unused = run(False)
+    assert used is not None and used.epoch == 3 and len(used._params) > 40 and unused is None
+    assert torch.equal(la[0], lb[0]), (la, lb)          # forward only: deterministic, so bit-identical
+    assert all(abs(a.item() - b.item()) <= 1e-5 * abs(b.item()) for a, b in zip(la, lb)), (la, lb)
+    assert ga.keys() == gb.keys()
+    for k in ga:
+        assert (ga[k] - gb[k]).abs().max().item() <= 2e-2 * gb[k].abs().max().item() + 1e-9, (k, (ga[k] - gb[k]).abs().max().item(), gb[k].abs().max().item())
+
+
+def test_weight_shadows_refuse_a_backward_after_the_weights_changed():
+    from sparse_vae_b200.core.linear import Linear, WeightShadows
+    dev = torch.device('cuda')
+    lin = Linear(512, 512).to(dev)
+    shadows = WeightShadows(lin)
+    x = torch.randn(2048, 512, device=dev, requires_grad=True)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        with shadows.step():
+            y = lin(x)
+        with torch.no_grad():
+            lin.weight.mul_(2.0)                    # an optimizer step between forward and backward ...
+        with shadows.step():                        # ... and another forward that refreshes the copies
+            lin(x)
+    with pytest.raises(RuntimeError, match='modified'):
+        y.sum().backward()
