@@ -40,6 +40,25 @@ def _token_weights(labels: Tensor, vocab: int, ignore_index: int = 0) -> Tensor:
     return valid / (n_chunks * per_chunk)[chunk_of]
 
 
+_ADDMM_F32_OUT = None          # does this torch build accumulate 16-bit GEMMs into an fp32 matrix (addmm.dtype_out)?
+
+
+def _accumulate_mm(acc: Tensor, a: Tensor, b: Tensor):
+    """acc (fp32) += a @ b for 16-bit a, b with fp32 accumulation, in the GEMM's own epilogue when the library
+    offers it (beta = 1) instead of a separate product and add."""
+    global _ADDMM_F32_OUT
+    if _ADDMM_F32_OUT is not False:
+        try:
+            torch.ops.aten.addmm.dtype_out(acc, a, b, torch.float32, out=acc)
+            _ADDMM_F32_OUT = True
+            return
+        except (RuntimeError, NotImplementedError, AttributeError):
+            if _ADDMM_F32_OUT:                  # worked before: a real error
+                raise
+            _ADDMM_F32_OUT = False
+    acc.add_(torch.mm(a, b, out_dtype=torch.float32))
+
+
 class _VocabNLL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hidden: Tensor, weight: Tensor, bias, labels: Tensor, token_w: Tensor, compute_dtype, row_chunk: int):
@@ -80,7 +99,7 @@ class _VocabNLL(torch.autograd.Function):
                 if compute_dtype == torch.float32:
                     dwb.addmm_(logits.t(), h_aug[r0:r1])
                 else:
-                    dwb.add_(torch.mm(logits.t(), h_aug[r0:r1], out_dtype=torch.float32))
+                    _accumulate_mm(dwb, logits.t(), h_aug[r0:r1])
             if db is not None:
                 db.add_(logits.sum(0, dtype=torch.float32))
         dw = dwb[:, :D] if need[1] else None
