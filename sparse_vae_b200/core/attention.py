@@ -20,7 +20,7 @@ from torch import nn, Tensor
 
 from .. import _native as N
 from .layer_norm import LayerNorm
-from .linear import Linear
+from .linear import Linear, linear3
 from .padded_tensor import PaddedTensor, split_padding
 from .residual import residual_add
 from .rotary_embedding import RotaryEmbedding
@@ -135,10 +135,14 @@ class Attention(nn.Module):
 
         if self.learned_queries is not None:
             q = self.learned_queries.expand(k.shape[0], *self.learned_queries.shape[1:])
+            k, v = self.k_linear(k), self.v_linear(v)
         else:
             q, _ = split_padding(q)
-            q = encode_position_rotary(self.q_linear(q), self.cache_index, max_pos=max_pos)
-        k, v = self.k_linear(k), self.v_linear(v)
+            if q is k and k is v and self.q_linear.bias is not None:        # self-attention: one input, three projections
+                q, k, v = linear3(q, self.q_linear, self.k_linear, self.v_linear)
+            else:
+                q, k, v = self.q_linear(q), self.k_linear(k), self.v_linear(v)
+            q = encode_position_rotary(q, self.cache_index, max_pos=max_pos)
         k = encode_position_rotary(k, self.cache_index, max_pos=max_pos)
         if self.kv_cache_length:
             k, v = self._update_kv_cache(k, v)

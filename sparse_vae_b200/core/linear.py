@@ -73,17 +73,89 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+class _Linear3Fn(torch.autograd.Function):
+    """q / k / v projections of one input (self-attention): three library GEMMs forward; backward accumulates the
+    three input-gradient products in the GEMM epilogue (beta = 1) instead of two extra element-wise adds."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, dtype: torch.dtype, shadows, *wb):
+        # wb = (w0, b0, w16_0, b16_0, w1, b1, w16_1, b16_1, w2, b2, w16_2, b16_2)
+        x16 = x.to(dtype)
+        outs, w16s = [], []
+        for i in range(3):
+            w, b, w16, b16 = wb[4 * i:4 * i + 4]
+            if w16 is None:
+                w16, b16 = w.to(dtype), b.to(dtype)
+            w16s.append(w16)
+            outs.append(F.linear(x16, w16, b16))
+        ctx.save_for_backward(x16, *w16s)
+        ctx.in_dtypes = (x.dtype, wb[0].dtype, wb[1].dtype)
+        ctx.shadows, ctx.epoch = shadows, (shadows.epoch if shadows is not None else 0)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        x16, *w16s = ctx.saved_tensors
+        if ctx.shadows is not None and ctx.shadows.epoch != ctx.epoch:
+            raise RuntimeError("a weight needed for this backward pass was modified (optimizer step?) after the forward "
+                               "pass that used its 16-bit shadow copy")
+        xd, wd, bd = ctx.in_dtypes
+        x2 = x16.reshape(-1, x16.shape[-1])
+        dx = None
+        grads = []
+        for i, (g, w16) in enumerate(zip(gs, w16s)):
+            dw = db = None
+            if g is not None:
+                g2 = g.reshape(-1, w16.shape[0])
+                if not g2.is_contiguous():
+                    g2 = g2.contiguous()
+                if ctx.needs_input_grad[0]:
+                    if dx is None:
+                        dx = torch.mm(g2, w16)
+                    else:
+                        dx.addmm_(g2, w16)
+                if ctx.needs_input_grad[3 + 4 * i]:
+                    dw = torch.mm(g2.t(), x2, out_dtype=torch.float32).to(wd)
+                if ctx.needs_input_grad[4 + 4 * i]:
+                    db = colsum(g2).to(bd)
+            grads += [dw, db, None, None]
+        return (dx.view(x16.shape).to(xd) if dx is not None else None, None, None, *grads)
+
+
+def linear3(x: Tensor, lin0: 'Linear', lin1: 'Linear', lin2: 'Linear'):
+    """(lin0(x), lin1(x), lin2(x)) -- the q / k / v projections of self-attention."""
+    if all(m._fused_ok(x) for m in (lin0, lin1, lin2)):
+        dtype = torch.get_autocast_dtype('cuda')
+        if dtype in (torch.bfloat16, torch.float16):
+            args, shadows = [], None
+            shs = [m._active_shadow(dtype) for m in (lin0, lin1, lin2)]
+            use = all(sh is not None for sh in shs)
+            for m, sh in zip((lin0, lin1, lin2), shs):
+                args += [m.weight, m.bias, sh[1] if use else None, sh[2] if use else None]
+            if use:
+                shadows = shs[0][0]
+            return _Linear3Fn.apply(x, dtype, shadows, *args)
+    return lin0(x), lin1(x), lin2(x)
+
+
 class Linear(nn.Linear):
     _shadow = None          # (WeightShadows, weight view, bias view | None), set by WeightShadows
 
+    def _fused_ok(self, x: Tensor) -> bool:
+        return bool(N.FUSED_EXTRAS and x.is_cuda and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
+                    and self.out_features % 8 == 0 and x.numel() >= _MIN_ROWS * self.in_features
+                    and (x.requires_grad or self.weight.requires_grad))
+
+    def _active_shadow(self, dtype):
+        sh = self._shadow
+        return sh if sh is not None and sh[0] is WeightShadows.ACTIVE and sh[1].dtype == dtype else None
+
     def forward(self, x: Tensor) -> Tensor:
-        if (N.FUSED_EXTRAS and x.is_cuda and torch.is_autocast_enabled('cuda') and torch.is_grad_enabled()
-                and self.out_features % 8 == 0 and x.numel() >= _MIN_ROWS * self.in_features
-                and (x.requires_grad or self.weight.requires_grad)):
+        if self._fused_ok(x):
             dtype = torch.get_autocast_dtype('cuda')
             if dtype in (torch.bfloat16, torch.float16):
-                sh = self._shadow
-                if sh is not None and sh[0] is WeightShadows.ACTIVE and sh[1].dtype == dtype:
+                sh = self._active_shadow(dtype)
+                if sh is not None:
                     return _LinearFn.apply(x, self.weight, self.bias, dtype, sh[1], sh[2], sh[0])
                 return _LinearFn.apply(x, self.weight, self.bias, dtype, None, None, None)
         return F.linear(x, self.weight, self.bias)

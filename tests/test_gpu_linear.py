@@ -143,3 +143,31 @@ def test_weight_shadows_refuse_a_backward_after_the_weights_changed():
             lin(x)
     with pytest.raises(RuntimeError, match='modified'):
         y.sum().backward()
+
+
+def test_linear3_matches_three_separate_projections():
+    """q / k / v projections of one input: outputs bit-identical, gradients equal up to the rounding of the summed
+    input gradient (GEMM-epilogue accumulation vs two bf16 adds)."""
+    from sparse_vae_b200.core.linear import Linear, _Linear3Fn, linear3
+    dev = torch.device('cuda')
+    torch.manual_seed(0)
+    lins = [Linear(512, 512).to(dev) for _ in range(3)]
+    x = torch.randn(4, 1024, 512, device=dev, requires_grad=True)
+    gs = [torch.randn(4, 1024, 512, device=dev) for _ in range(3)]
+
+    def run(fn):
+        x.grad = None
+        for m in lins:
+            m.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            outs = fn()
+        torch.autograd.backward(outs, [g.to(o.dtype) for g, o in zip(gs, outs)])
+        return [o.detach().clone() for o in outs], x.grad.clone(), [(m.weight.grad.clone(), m.bias.grad.clone()) for m in lins]
+
+    o1, dx1, p1 = run(lambda: linear3(x, *lins))
+    assert isinstance(linear3(x.detach().requires_grad_(), *lins)[0].grad_fn, type(None)) is False
+    o2, dx2, p2 = run(lambda: tuple(m(x) for m in lins))
+    assert all(torch.equal(a, b) for a, b in zip(o1, o2))
+    assert (dx1 - dx2).abs().max().item() <= 2e-2 * dx2.abs().max().item()
+    for (w1, b1), (w2, b2) in zip(p1, p2):
+        assert torch.equal(w1, w2) and torch.equal(b1, b2)
