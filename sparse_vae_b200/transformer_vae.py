@@ -141,8 +141,10 @@ class TransformerVAE(TransformerLanguageModel, ContinuousVAE):
         padding = x_pad if padding is None else padding
         use_checkpoint = self.hparams.grad_checkpointing and x.requires_grad
         for i, (layer, project) in enumerate(zip(self.decoder_layers, self.z_projections)):
-            if N.FUSED_EXTRAS and i > 0 and x.is_cuda and x.requires_grad and not x.is_leaf and not use_checkpoint:
-                x = _ReplaceFirstPosition.apply(x, project(z).to(x.dtype))       # x is the previous layer's own output
+            if N.FUSED_EXTRAS and x.is_cuda and x.requires_grad and not use_checkpoint:
+                # layers > 0: x is the previous layer's own output, nobody else reads it; layer 0: the caller's
+                # embedding must stay intact, so the row goes into a copy (a flat copy, not cat's strided gather)
+                x = _ReplaceFirstPosition.apply(x if i > 0 and not x.is_leaf else x.clone(), project(z).to(x.dtype))
             else:
                 x = torch.cat([project(z).to(x.dtype), x[..., 1:, :]], dim=-2)   # z takes the [CLS] position
             x = checkpoint(layer, x, None, padding, use_reentrant=False) if use_checkpoint else layer(x, padding=padding)
