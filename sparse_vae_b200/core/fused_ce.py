@@ -12,13 +12,15 @@ to the autocast dtype by the GEMM, fp32 log-softmax on those rounded logits, gra
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn, Tensor
 
 from .. import _native as N
 
-ROW_CHUNK = 4096
+ROW_CHUNK = int(os.environ.get('SVAE_CE_ROW_CHUNK', 16384))      # rows of logits alive at a time ([rows, vocab] 16-bit)
 
 
 def supported(hidden: Tensor, linear: nn.Linear) -> bool:
@@ -121,7 +123,7 @@ class _VocabNLL(torch.autograd.Function):
         return g_h, g_w, g_b, None, None, None, None
 
 
-def fused_vocab_nll(hidden: Tensor, linear: nn.Linear, labels: Tensor, row_chunk: int = ROW_CHUNK) -> Tensor:
+def fused_vocab_nll(hidden: Tensor, linear: nn.Linear, labels: Tensor, row_chunk: int = None) -> Tensor:
     """`robust_cross_entropy(linear(hidden)[..., :-1, :], labels)` for hidden [B, L, D] and labels [B, L-1]
     (the reference's next-token objective: position s predicts token s+1; padding id 0 ignored)."""
     B, L, _ = hidden.shape
@@ -136,5 +138,6 @@ def fused_vocab_nll(hidden: Tensor, linear: nn.Linear, labels: Tensor, row_chunk
     compute_dtype = torch.get_autocast_dtype('cuda') if torch.is_autocast_enabled('cuda') else hidden.dtype
     if compute_dtype not in (torch.float32, torch.bfloat16, torch.float16):
         raise ValueError(f"fused_vocab_nll: unsupported dtype {compute_dtype}")
-    loss, _ = _VocabNLL.apply(hidden, linear.weight, linear.bias, labels_full, token_w_full, compute_dtype, row_chunk)
+    loss, _ = _VocabNLL.apply(hidden, linear.weight, linear.bias, labels_full, token_w_full, compute_dtype,
+                              row_chunk or ROW_CHUNK)
     return loss
