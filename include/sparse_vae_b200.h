@@ -208,10 +208,14 @@ SVAE_API int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t vo
 /* ---- bias gradient of the decoder blocks' nn.Linear layers (reference core/attention.py:33-39, ------
  *      core/transformer_layer.py:20-24): out[c] = sum_r x[r, c], fp32 accumulation, deterministic two-stage sum. */
 /* x: [rows, n] (dtype), row stride ld elements, n % 8 == 0; out: fp32 [n];
- * workspace: device scratch of svae_colsum_workspace_floats(rows, n) floats. */
+ * workspace: device scratch of svae_colsum_workspace_floats(rows, n) floats.
+ * counters: NULL (two launches) or svae_colsum_counters(n) device uint32 that are ZERO on entry; they are zero again
+ * when the launch has run, so one array can be reused by consecutive calls on ONE stream (not by concurrent ones):
+ * the last block of each column group sums the partial results, in a fixed order, inside the same launch. */
 SVAE_API int64_t svae_colsum_workspace_floats(int64_t rows, int32_t n);
+SVAE_API int32_t svae_colsum_counters(int32_t n);
 SVAE_API int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, int64_t ld, float* out, float* workspace,
-                int64_t workspace_floats, void* stream);
+                int64_t workspace_floats, uint32_t* counters, void* stream);
 
 /* ---- rotary position encoding of q / k (reference core/attention.py:194-208) ---- */
 /* x, out: [rows, d_model] contiguous (dtype), row r sits at position r % seq_len; cos / sin tables: [seq_len,

@@ -34,7 +34,7 @@ EXPORTS = (
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
     'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench', 'svae_debug_set_bwd_timeline',
     'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
-    'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum',
+    'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum_counters', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
     'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
     'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast',
@@ -122,7 +122,9 @@ def _load() -> C.CDLL:
     lib.svae_colsum_workspace_floats.restype = i64
     lib.svae_colsum_workspace_floats.argtypes = [i64, i32]
     lib.svae_colsum.restype = C.c_int
-    lib.svae_colsum.argtypes = [vp, i32, i64, i32, i64, vp, vp, i64, vp]
+    lib.svae_colsum.argtypes = [vp, i32, i64, i32, i64, vp, vp, i64, vp, vp]
+    lib.svae_colsum_counters.restype = i32
+    lib.svae_colsum_counters.argtypes = [i32]
     lib.svae_rotary.restype = C.c_int
     lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
     lib.svae_decode_attn_supported.restype = C.c_int

@@ -28,14 +28,24 @@ from ..fused_optim import _PtrList
 _MIN_ROWS = 1024
 
 
+_COLSUM_COUNTERS: dict = {}          # (device, stream) -> zeroed uint32 tickets for the single-launch column sum
+
+
 def colsum(x2d: Tensor) -> Tensor:
-    """fp32 column sums of a [rows, n] CUDA matrix (unit inner stride, n % 8 == 0)."""
+    """fp32 column sums of a [rows, n] CUDA matrix (unit inner stride, n % 8 == 0), one launch."""
     rows, n = x2d.shape
     out = torch.empty(n, device=x2d.device, dtype=torch.float32)
     ws_floats = N.lib.svae_colsum_workspace_floats(rows, n)
     ws = torch.empty(ws_floats, device=x2d.device, dtype=torch.float32)
+    stream = N.current_stream(x2d.device)
+    # the kernel leaves its tickets at zero, so one array serves every call issued on the same stream
+    key = (x2d.device, stream)
+    counters = _COLSUM_COUNTERS.get(key)
+    if counters is None or counters.numel() < N.lib.svae_colsum_counters(n):
+        counters = _COLSUM_COUNTERS[key] = torch.zeros(max(1024, N.lib.svae_colsum_counters(n)), device=x2d.device,
+                                                       dtype=torch.int32)
     N.check(N.lib.svae_colsum(x2d.data_ptr(), N.svae_dtype(x2d.dtype), rows, n, x2d.stride(0), out.data_ptr(),
-                              ws.data_ptr(), ws_floats, N.current_stream(x2d.device)), 'svae_colsum')
+                              ws.data_ptr(), ws_floats, counters.data_ptr(), stream), 'svae_colsum')
     return out
 
 

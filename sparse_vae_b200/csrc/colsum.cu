@@ -2,7 +2,8 @@
 // (reference core/attention.py:33-39 q/k/v/output_linear, core/transformer_layer.py:20-24 ffn) in the backward pass.
 // ATen's generic reduction reaches ~1.6 TB/s on [65536, 512] bf16; this is a plain two-stage column reduction:
 // stage 1, block = 32 sixteen-byte column vectors x 8 row lanes walking a slab of rows (coalesced 512-byte
-// segments), fp32 accumulation, partial[slab][n]; stage 2 sums the slabs in a fixed order (deterministic).
+// segments), fp32 accumulation, partial[slab][n]; stage 2 sums the slabs in a fixed order (deterministic) -- either a
+// second small launch or, given a zeroed counter per column group, the last block of the group to finish (one launch).
 // HBM-bound: rows * n * sizeof(T) bytes read.
 #include "common.cuh"
 
@@ -40,7 +41,8 @@ template <> struct Vec8<__half> {
 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int n,
-                                                             float* __restrict__ partial) {
+                                                             float* __restrict__ partial, unsigned* __restrict__ counters,
+                                                             float* __restrict__ out) {
   __shared__ float red[8][32][9];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int vec = blockIdx.x * 32 + cx;              // 8-column vector index
@@ -67,6 +69,37 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
       partial[(int64_t)blockIdx.y * n + vec * 8 + e] = t;
     }
   }
+  if (counters == nullptr) return;                   // two-launch mode: colsum_final_kernel sums the slabs
+  // single-launch mode: the LAST block of this column group to finish sums the slabs, always in slab order, so the
+  // result does not depend on which block that is; it leaves the counter at zero for the next launch
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (ok)
+    for (int b = ry; b < (int)gridDim.y; b += 8) {
+      const float4 u = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)b * n + vec * 8));
+      const float4 w = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)b * n + vec * 8 + 4));
+      acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w; acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
+    }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
+  __syncthreads();
+  if (ry == 0 && ok) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][cx][e];
+      out[vec * 8 + e] = t;
+    }
+  }
+  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int slabs, int n,
@@ -101,8 +134,10 @@ using namespace svae;
 
 extern "C" int64_t svae_colsum_workspace_floats(int64_t rows, int32_t n) { return (int64_t)colsum_slabs(rows, n) * n; }
 
+extern "C" int32_t svae_colsum_counters(int32_t n) { return (n / 8 + 31) / 32; }
+
 extern "C" int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, int64_t ld, float* out, float* workspace,
-                           int64_t workspace_floats, void* stream) {
+                           int64_t workspace_floats, uint32_t* counters, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SVAE_REQUIRE(x && out && workspace && rows >= 0, SVAE_ERR_INVALID, "svae_colsum: null argument");
   SVAE_REQUIRE(n > 0 && n % 8 == 0 && ld >= n && ld % 8 == 0, SVAE_ERR_INVALID, "svae_colsum: n and ld must be multiples of 8");
@@ -111,12 +146,14 @@ extern "C" int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n
   SVAE_REQUIRE(workspace_floats >= (int64_t)slabs * n, SVAE_ERR_INVALID, "svae_colsum: workspace too small");
   dim3 grid((n / 8 + 31) / 32, slabs);
   ScopedKernelTimer timer("colsum", st);
-  if (dtype == SVAE_DTYPE_F32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, n, workspace);
-  else if (dtype == SVAE_DTYPE_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, n, workspace);
-  else if (dtype == SVAE_DTYPE_F16) colsum_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, ld, rows, n, workspace);
+  if (dtype == SVAE_DTYPE_F32) colsum_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ld, rows, n, workspace, counters, out);
+  else if (dtype == SVAE_DTYPE_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, n, workspace, counters, out);
+  else if (dtype == SVAE_DTYPE_F16) colsum_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, ld, rows, n, workspace, counters, out);
   else SVAE_REQUIRE(false, SVAE_ERR_INVALID, "svae_colsum: dtype %d", dtype);
   SVAE_CUDA_CHECK(cudaGetLastError());
-  colsum_final_kernel<<<(n + 31) / 32, 256, 0, st>>>(workspace, slabs, n, out);
-  SVAE_CUDA_CHECK(cudaGetLastError());
+  if (counters == nullptr) {
+    colsum_final_kernel<<<(n + 31) / 32, 256, 0, st>>>(workspace, slabs, n, out);
+    SVAE_CUDA_CHECK(cudaGetLastError());
+  }
   return SVAE_OK;
 }

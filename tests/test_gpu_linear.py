@@ -171,3 +171,23 @@ def test_linear3_matches_three_separate_projections():
     assert (dx1 - dx2).abs().max().item() <= 2e-2 * dx2.abs().max().item()
     for (w1, b1), (w2, b2) in zip(p1, p2):
         assert torch.equal(w1, w2) and torch.equal(b1, b2)
+
+
+@pytest.mark.parametrize('rows,n', [(65536, 512), (777, 2048), (5, 8)])
+def test_colsum_single_launch_equals_two_launch(rows, n):
+    """The last-block reduction sums the slabs in the same fixed order as the separate second launch: bit-identical,
+    and the ticket counters are back at zero afterwards (reusable)."""
+    from sparse_vae_b200 import _native as N
+    dev = torch.device('cuda')
+    x = torch.randn(rows, n, device=dev).to(torch.bfloat16)
+    ws_floats = N.lib.svae_colsum_workspace_floats(rows, n)
+    ws = torch.empty(ws_floats, device=dev)
+    counters = torch.zeros(N.lib.svae_colsum_counters(n), device=dev, dtype=torch.int32)
+    outs = []
+    for ctr in (None, counters, counters):
+        out = torch.empty(n, device=dev)
+        N.check(N.lib.svae_colsum(x.data_ptr(), N.svae_dtype(x.dtype), rows, n, n, out.data_ptr(), ws.data_ptr(), ws_floats,
+                                  None if ctr is None else ctr.data_ptr(), N.current_stream(dev)), 'svae_colsum')
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and int(counters.abs().sum()) == 0
+    assert (outs[0].double() - x.double().sum(0)).abs().max().item() <= 1e-3 * max(1.0, x.double().sum(0).abs().max().item())
