@@ -250,6 +250,15 @@ SVAE_API int svae_decode_attn(const void* q, const void* k, const void* v, const
  * x, out fp32 and h 16-bit, numel % 8 == 0, 16-byte aligned; out == x is allowed. */
 SVAE_API int svae_residual_add(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, void* stream);
 
+/* The same with dropout on the branch (training mode of core/transformer_layer.py:61 `x + self.dropout(ffn(...))`):
+ * out = x + dropout_p(h), h scaled by 1/(1-p) and rounded to its dtype where kept.  The keep mask is a pure function of
+ * (seed, offset, element index) -- Philox4x32-10 -- and is regenerated, not stored, by svae_dropout_branch_grad:
+ * dh = dtype(dtype(g) / (1-p)) where kept, 0 elsewhere.  The caller advances its generator offset by 4 per launch. */
+SVAE_API int svae_residual_dropout_add(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, float p,
+                              uint64_t seed, uint64_t offset, void* stream);
+SVAE_API int svae_dropout_branch_grad(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
+                             uint64_t offset, void* stream);
+
 /* Decoding step glue: x (fp32 residual stream, updated in place) += h, then y = LayerNorm(x) with the arithmetic of
  * svae_layernorm_fwd (reference core/transformer_layer.py:35-61: `x = x + h` followed by the next sub-layer's norm). */
 SVAE_API int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,

@@ -37,7 +37,8 @@ EXPORTS = (
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum_counters', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
     'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
-    'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast',
+    'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast', 'svae_residual_dropout_add',
+    'svae_dropout_branch_grad',
 )
 
 
@@ -131,6 +132,10 @@ def _load() -> C.CDLL:
     lib.svae_decode_attn_supported.argtypes = [i32, i32, i32]
     lib.svae_decode_attn.restype = C.c_int
     lib.svae_decode_attn.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i64, i32, C.c_float, vp]
+    lib.svae_residual_dropout_add.restype = C.c_int
+    lib.svae_residual_dropout_add.argtypes = [vp, vp, i32, vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
+    lib.svae_dropout_branch_grad.restype = C.c_int
+    lib.svae_dropout_branch_grad.argtypes = [vp, vp, i32, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
     lib.svae_residual_add.restype = C.c_int
     lib.svae_residual_add.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.svae_residual_layernorm.restype = C.c_int

@@ -22,7 +22,7 @@ from .. import _native as N
 from .layer_norm import LayerNorm
 from .linear import Linear, linear3
 from .padded_tensor import PaddedTensor, split_padding
-from .residual import residual_add
+from .residual import residual_add, residual_dropout_add
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
 
@@ -270,7 +270,7 @@ class TransformerLayer(nn.Module):
                                      padding=context_padding)
             x = residual_add(x, h)
 
-        return residual_add(x, self.dropout(self.ffn(self.ffn_layer_norm(x))))
+        return residual_dropout_add(x, self.ffn(self.ffn_layer_norm(x)), self.dropout)
 
 
 class Perceiver(nn.Module):

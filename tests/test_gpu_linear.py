@@ -191,3 +191,41 @@ def test_colsum_single_launch_equals_two_launch(rows, n):
         outs.append(out)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and int(counters.abs().sum()) == 0
     assert (outs[0].double() - x.double().sum(0)).abs().max().item() <= 1e-3 * max(1.0, x.double().sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_residual_dropout_add_mask_scaling_and_gradients(dtype):
+    """x + dropout(h): kept elements carry dtype(h / (1-p)), the rest nothing; the backward pass regenerates the same
+    mask; keep rate and independence from torch's own dropout stream are statistical."""
+    from sparse_vae_b200.core.residual import _ResidualDropoutAddFn, residual_dropout_add
+    dev = torch.device('cuda')
+    torch.manual_seed(1)
+    drop = torch.nn.Dropout(p=0.1).train()
+    shape = (8, 4096, 512)
+    x = torch.randn(*shape, device=dev, requires_grad=True)
+    h = (torch.randn(*shape, device=dev) + 3.0).to(dtype).requires_grad_()        # no zeros: the mask is visible in out - x
+    before = torch.cuda.default_generators[0].get_offset()
+    out = residual_dropout_add(x, h, drop)
+    assert isinstance(out.grad_fn, _ResidualDropoutAddFn._backward_cls)
+    assert torch.cuda.default_generators[0].get_offset() == before + 4
+    branch = (out - x).detach()
+    kept = branch != 0
+    rate = kept.float().mean().item()
+    assert abs(rate - 0.9) < 2e-3, rate
+    want = (h.detach().float() * (1.0 / (1.0 - 0.1))).to(dtype).float()
+    # out = fp32(x + branch): compare the branch through the same addition
+    assert torch.equal(out.detach()[kept], (x.detach() + want)[kept]) and torch.equal(out.detach()[~kept], x.detach()[~kept])
+    g = torch.randn(*shape, device=dev)
+    out.backward(g)
+    assert torch.equal(x.grad, g)
+    want_dh = (g.to(dtype).float() * (1.0 / (1.0 - 0.1))).to(dtype)
+    assert torch.equal(h.grad[kept], want_dh[kept]) and int(h.grad[~kept].abs().sum()) == 0
+    # a second call draws a different mask; neighbouring elements are not correlated
+    out2 = residual_dropout_add(x, h, drop)
+    kept2 = (out2 - x).detach() != 0
+    both = (kept & kept2).float().mean().item()
+    assert abs(both - 0.81) < 3e-3, both
+    pair = (kept[..., 1:] & kept[..., :-1]).float().mean().item()
+    assert abs(pair - 0.81) < 3e-3, pair
+    # eval mode: the plain residual add
+    assert torch.equal(residual_dropout_add(x, h, drop.eval()), x + h)
