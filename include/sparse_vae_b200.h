@@ -192,10 +192,12 @@ SVAE_API int svae_layernorm_fwd(const void* x, int32_t x_dtype, const float* gam
                        int32_t n, float eps, void* y, int32_t y_dtype, float* mean, float* rstd, void* stream);
 SVAE_API int64_t svae_layernorm_bwd_workspace_floats(int64_t rows, int32_t n);
 /* dx (x_dtype, may be NULL), dgamma / dbeta (fp32 [n], may be NULL) from dy (y_dtype) in ONE pass over x and dy;
+ * dx_residual (x_dtype, may be NULL; may equal dx) is added to dx: the gradient that reaches x through the residual
+ * connection around the norm (core/transformer_layer.py:35-61), saving autograd's separate accumulation pass;
  * workspace: device scratch of svae_layernorm_bwd_workspace_floats(rows, n) floats (deterministic two-level sum). */
 SVAE_API int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, int32_t x_dtype, const float* gamma,
-                       const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, float* dgamma,
-                       float* dbeta, float* workspace, int64_t workspace_floats, void* stream);
+                       const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, const void* dx_residual,
+                       float* dgamma, float* dbeta, float* workspace, int64_t workspace_floats, void* stream);
 
 /* ---- vocabulary cross-entropy (reference core/language_model.py:98-113,161-170) ---- */
 /* logits: [rows, vocab] (dtype), row stride ld elements, vocab = 8192*k (k <= 4).  nll[r] = logsumexp(row) -

@@ -115,7 +115,7 @@ def _load() -> C.CDLL:
     lib.svae_layernorm_bwd_workspace_floats.restype = i64
     lib.svae_layernorm_bwd_workspace_floats.argtypes = [i64, i32]
     lib.svae_layernorm_bwd.restype = C.c_int
-    lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, i64, vp]
+    lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.svae_vocab_ce_supported.restype = C.c_int
     lib.svae_vocab_ce_supported.argtypes = [i32]
     lib.svae_vocab_ce.restype = C.c_int

@@ -259,7 +259,10 @@ class TransformerLayer(nn.Module):
                 context_padding: Optional[Tensor] = None) -> Tensor:
         x, x_pad = split_padding(x)
         padding = x_pad if padding is None else padding
-        h = self.attn_layer_norm(x)
+        if self.attention.learned_queries is None:
+            x, h = self.attn_layer_norm.fork(x)              # x feeds the norm AND the residual around the attention
+        else:
+            h = self.attn_layer_norm(x)
         h = self.attention(h, h, h, padding=padding)
         x = residual_add(x, h) if x.shape == h.shape else h  # learned queries change the length: no residual
 
@@ -270,7 +273,8 @@ class TransformerLayer(nn.Module):
                                      padding=context_padding)
             x = residual_add(x, h)
 
-        return residual_dropout_add(x, self.ffn(self.ffn_layer_norm(x)), self.dropout)
+        x, h = self.ffn_layer_norm.fork(x)
+        return residual_dropout_add(x, self.ffn(h), self.dropout)
 
 
 class Perceiver(nn.Module):

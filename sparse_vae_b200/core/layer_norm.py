@@ -38,22 +38,52 @@ class _LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy: Tensor):
-        x2, weight, stats = ctx.saved_tensors
-        rows, n = x2.shape
-        dy2 = dy.reshape(rows, n)
-        if not dy2.is_contiguous():
-            dy2 = dy2.contiguous()
-        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-        dx = torch.empty_like(x2) if need_x else None
-        dgb = torch.empty((2, n), device=x2.device, dtype=torch.float32) if (need_w or need_b) else None
-        ws_floats = N.lib.svae_layernorm_bwd_workspace_floats(rows, n)
-        ws = torch.empty(ws_floats, device=x2.device, dtype=torch.float32)
-        N.check(N.lib.svae_layernorm_bwd(dy2.data_ptr(), N.svae_dtype(dy2.dtype), x2.data_ptr(), N.svae_dtype(x2.dtype),
-                                         weight.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), rows, n, N.ptr(dx),
-                                         dgb[0].data_ptr() if need_w else None, dgb[1].data_ptr() if need_b else None,
-                                         ws.data_ptr(), ws_floats, N.current_stream(x2.device)), 'svae_layernorm_bwd')
-        return (dx.view(ctx.x_shape) if need_x else None, dgb[0] if need_w else None, dgb[1] if need_b else None,
-                None, None)
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, None)
+        return dx, dgamma, dbeta, None, None
+
+
+def _layer_norm_backward(ctx, dy: Tensor, dres):
+    """One pass over x and dy: dx (+ dres, the gradient arriving around the norm), dgamma, dbeta."""
+    x2, weight, stats = ctx.saved_tensors
+    rows, n = x2.shape
+    dy2 = dy.reshape(rows, n)
+    if not dy2.is_contiguous():
+        dy2 = dy2.contiguous()
+    need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+    dx = torch.empty_like(x2) if need_x else None
+    dgb = torch.empty((2, n), device=x2.device, dtype=torch.float32) if (need_w or need_b) else None
+    ws_floats = N.lib.svae_layernorm_bwd_workspace_floats(rows, n)
+    ws = torch.empty(ws_floats, device=x2.device, dtype=torch.float32)
+    N.check(N.lib.svae_layernorm_bwd(dy2.data_ptr(), N.svae_dtype(dy2.dtype), x2.data_ptr(), N.svae_dtype(x2.dtype),
+                                     weight.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), rows, n, N.ptr(dx),
+                                     N.ptr(dres) if need_x else None, dgb[0].data_ptr() if need_w else None,
+                                     dgb[1].data_ptr() if need_b else None, ws.data_ptr(), ws_floats,
+                                     N.current_stream(x2.device)), 'svae_layernorm_bwd')
+    return (dx.view(ctx.x_shape) if need_x else None, dgb[0] if need_w else None, dgb[1] if need_b else None)
+
+
+class _NormForkFn(torch.autograd.Function):
+    """(x, LayerNorm(x)) for the pre-norm residual blocks (reference core/transformer_layer.py:35-61: x feeds both the
+    norm of a sub-layer and the residual connection around it).  Backward adds the two gradients of x inside the
+    LayerNorm-backward pass instead of leaving the sum to a separate accumulation kernel."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias, eps: float, out_dtype: torch.dtype):
+        y = _LayerNormFn.forward(ctx, x, weight, bias, eps, out_dtype)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_skip, dy):
+        if dy is None:
+            return g_skip, None, None, None, None
+        dres = None
+        if g_skip is not None and ctx.needs_input_grad[0]:
+            x2 = ctx.saved_tensors[0]
+            dres = g_skip.reshape(x2.shape)
+            if dres.dtype != x2.dtype or not dres.is_contiguous():
+                dres = dres.to(x2.dtype).contiguous()
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, dres)
+        return dx, dgamma, dbeta, None, None
 
 
 _PAIRS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torch.float32, torch.float16),
@@ -64,7 +94,7 @@ _PAIRS = {(torch.float32, torch.float32), (torch.float32, torch.bfloat16), (torc
 class LayerNorm(nn.LayerNorm):
     emit_autocast_dtype: bool = True
 
-    def forward(self, x: Tensor) -> Tensor:
+    def _fused_out_dtype(self, x: Tensor):
         fused = (N.FUSED_EXTRAS and x.is_cuda and self.elementwise_affine and len(self.normalized_shape) == 1 and x.numel() > 0
                  and self.weight.dtype == torch.float32 and N.lib.svae_layernorm_supported(x.shape[-1]))
         if fused:
@@ -72,5 +102,19 @@ class LayerNorm(nn.LayerNorm):
             if torch.is_autocast_enabled('cuda'):
                 out_dtype = torch.get_autocast_dtype('cuda') if self.emit_autocast_dtype else torch.float32
             if (x.dtype, out_dtype) in _PAIRS:
-                return _LayerNormFn.apply(x, self.weight, self.bias, self.eps, out_dtype)
+                return out_dtype
+        return None
+
+    def forward(self, x: Tensor) -> Tensor:
+        out_dtype = self._fused_out_dtype(x)
+        if out_dtype is not None:
+            return _LayerNormFn.apply(x, self.weight, self.bias, self.eps, out_dtype)
         return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+
+    def fork(self, x: Tensor):
+        """(x, self(x)) for a pre-norm block whose residual connection goes around this norm: use the returned x for
+        the skip path, so that backward sums the two gradients of x inside the LayerNorm-backward kernel."""
+        out_dtype = self._fused_out_dtype(x)
+        if out_dtype is not None and torch.is_grad_enabled() and x.requires_grad:
+            return _NormForkFn.apply(x, self.weight, self.bias, self.eps, out_dtype)
+        return x, self(x)

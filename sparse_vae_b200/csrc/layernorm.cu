@@ -152,7 +152,7 @@ template <typename TX, typename TY, int VPT>
 __global__ void __launch_bounds__(kLnThreads)
 layernorm_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
-                     float* __restrict__ partial, int64_t rows) {
+                     const TX* __restrict__ dres, float* __restrict__ partial, int64_t rows) {
   constexpr int N = 128 * VPT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + warp;
@@ -190,6 +190,12 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const 
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = rstd * (d[i][e] - c1 - xh[i][e] * c2);
+        if (dres) {                                  // gradient arriving through the residual path around this norm
+          float a[4];
+          Vec4<TX>::load(dres + r * N + (i * 32 + lane) * 4, a);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] += a[e];
+        }
         Vec4<TX>::store(dx + r * N + (i * 32 + lane) * 4, o);
       }
     }
@@ -257,9 +263,9 @@ static int launch_fwd(int vpt, const void* x, const float* gamma, const float* b
 
 template <typename TX, typename TY>
 static int launch_bwd(int vpt, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      void* dx, float* partial, int grid, int64_t rows, cudaStream_t st) {
+                      void* dx, const void* dres, float* partial, int grid, int64_t rows, cudaStream_t st) {
 #define SVAE_LN_BWD(V)                                                                                         \
-  case V: layernorm_bwd_kernel<TX, TY, V><<<grid, kLnThreads, 0, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, partial, rows); break
+  case V: layernorm_bwd_kernel<TX, TY, V><<<grid, kLnThreads, 0, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, (const TX*)dres, partial, rows); break
   switch (vpt) { SVAE_LN_BWD(1); SVAE_LN_BWD(2); SVAE_LN_BWD(4); SVAE_LN_BWD(8); default: return SVAE_ERR_UNSUPPORTED; }
 #undef SVAE_LN_BWD
   SVAE_CUDA_CHECK(cudaGetLastError());
@@ -311,8 +317,9 @@ extern "C" int svae_layernorm_fwd(const void* x, int32_t x_dtype, const float* g
 }
 
 extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, int32_t x_dtype, const float* gamma,
-                                  const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, float* dgamma,
-                                  float* dbeta, float* workspace, int64_t workspace_floats, void* stream) {
+                                  const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx,
+                                  const void* dx_residual, float* dgamma, float* dbeta, float* workspace,
+                                  int64_t workspace_floats, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SVAE_REQUIRE(dy && x && gamma && mean && rstd && workspace && rows >= 0, SVAE_ERR_INVALID, "svae_layernorm_bwd: null argument");
   SVAE_REQUIRE(ln_shape_ok(n), SVAE_ERR_UNSUPPORTED, "svae_layernorm_bwd: width %d not in {128, 256, 512, 1024}", n);
@@ -320,7 +327,7 @@ extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x
   SVAE_REQUIRE(workspace_floats >= (int64_t)grid * 2 * n, SVAE_ERR_INVALID, "svae_layernorm_bwd: workspace too small");
   ScopedKernelTimer timer("layernorm_bwd", st);
   auto run = [&]() -> int {
-    SVAE_LN_DISPATCH(launch_bwd, n / 128, dy, x, gamma, mean, rstd, dx, workspace, grid, rows, st);
+    SVAE_LN_DISPATCH(launch_bwd, n / 128, dy, x, gamma, mean, rstd, dx, dx_residual, workspace, grid, rows, st);
     SVAE_REQUIRE(false, SVAE_ERR_UNSUPPORTED, "svae_layernorm_bwd: dtype pair (%d -> %d) not supported", x_dtype, y_dtype);
   };
   int rc = run();

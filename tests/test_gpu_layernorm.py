@@ -86,3 +86,35 @@ def test_layernorm_unsupported_width_uses_aten():
     ln = LayerNorm(96).cuda()
     x = torch.randn(8, 96, device='cuda')
     torch.testing.assert_close(ln(x), F.layer_norm(x, (96,), ln.weight, ln.bias, ln.eps))
+
+
+@pytest.mark.parametrize('autocast', [True, False])
+def test_norm_fork_matches_separate_norm_and_skip(autocast):
+    """(x, LN(x)) with the skip path's gradient added inside the LayerNorm-backward kernel == plain autograd."""
+    from sparse_vae_b200.core.layer_norm import LayerNorm, _NormForkFn
+    dev = torch.device('cuda')
+    torch.manual_seed(4)
+    ln = LayerNorm(512).to(dev)
+    with torch.no_grad():
+        ln.weight.normal_(1, 0.1)
+        ln.bias.normal_(0, 0.1)
+    x = torch.randn(6, 300, 512, device=dev, requires_grad=True)
+    w = torch.randn(512, 512, device=dev) * 0.05
+    g = torch.randn(6, 300, 512, device=dev)
+
+    def run(fork):
+        x.grad = None
+        ln.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+            if fork:
+                skip, y = ln.fork(x)
+                assert isinstance(y.grad_fn, _NormForkFn._backward_cls)
+            else:
+                skip, y = x, ln(x)
+            out = skip + (y @ w.to(y.dtype)).float()
+        out.backward(g)
+        return out.detach().clone(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert (a[1] - b[1]).abs().max().item() <= 1e-6 * b[1].abs().max().item()
