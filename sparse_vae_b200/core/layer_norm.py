@@ -38,13 +38,14 @@ class _LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy: Tensor):
-        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, None)
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, ctx.saved_tensors, dy, None)
         return dx, dgamma, dbeta, None, None
 
 
-def _layer_norm_backward(ctx, dy: Tensor, dres):
-    """One pass over x and dy: dx (+ dres, the gradient arriving around the norm), dgamma, dbeta."""
-    x2, weight, stats = ctx.saved_tensors
+def _layer_norm_backward(ctx, saved, dy: Tensor, dres):
+    """One pass over x and dy: dx (+ dres, the gradient arriving around the norm), dgamma, dbeta.
+    `saved` = ctx.saved_tensors, read exactly once by the caller (activation checkpointing insists on that)."""
+    x2, weight, stats = saved
     rows, n = x2.shape
     dy2 = dy.reshape(rows, n)
     if not dy2.is_contiguous():
@@ -76,13 +77,14 @@ class _NormForkFn(torch.autograd.Function):
     def backward(ctx, g_skip, dy):
         if dy is None:
             return g_skip, None, None, None, None
+        saved = ctx.saved_tensors
         dres = None
         if g_skip is not None and ctx.needs_input_grad[0]:
-            x2 = ctx.saved_tensors[0]
+            x2 = saved[0]
             dres = g_skip.reshape(x2.shape)
             if dres.dtype != x2.dtype or not dres.is_contiguous():
                 dres = dres.to(x2.dtype).contiguous()
-        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, dres)
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, saved, dy, dres)
         return dx, dgamma, dbeta, None, None
 
 
