@@ -21,7 +21,7 @@ from torch import nn, Tensor
 from .. import _native as N
 from .layer_norm import LayerNorm
 from .linear import Linear, linear3
-from .padded_tensor import PaddedTensor, split_padding
+from .padded_tensor import split_padding
 from .residual import residual_add, residual_dropout_add
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
