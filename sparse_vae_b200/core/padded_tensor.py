@@ -11,7 +11,6 @@ from __future__ import annotations
 
 from typing import Optional
 
-import torch
 from torch import Tensor
 
 
