@@ -194,10 +194,13 @@ SVAE_API int64_t svae_layernorm_bwd_workspace_floats(int64_t rows, int32_t n);
 /* dx (x_dtype, may be NULL), dgamma / dbeta (fp32 [n], may be NULL) from dy (y_dtype) in ONE pass over x and dy;
  * dx_residual (x_dtype, may be NULL; may equal dx) is added to dx: the gradient that reaches x through the residual
  * connection around the norm (core/transformer_layer.py:35-61), saving autograd's separate accumulation pass;
+ * dx_low (y_dtype, may be NULL) receives the same dx rounded to y_dtype -- the gradient of a 16-bit branch that was
+ * added to the stream right before this norm (svae_residual_layernorm);
  * workspace: device scratch of svae_layernorm_bwd_workspace_floats(rows, n) floats (deterministic two-level sum). */
 SVAE_API int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, int32_t x_dtype, const float* gamma,
                        const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx, const void* dx_residual,
-                       float* dgamma, float* dbeta, float* workspace, int64_t workspace_floats, void* stream);
+                       void* dx_low, float* dgamma, float* dbeta, float* workspace, int64_t workspace_floats,
+                       void* stream);
 
 /* ---- vocabulary cross-entropy (reference core/language_model.py:98-113,161-170) ---- */
 /* logits: [rows, vocab] (dtype), row stride ld elements, vocab = 8192*k (k <= 4).  nll[r] = logsumexp(row) -
@@ -261,10 +264,12 @@ SVAE_API int svae_residual_dropout_add(const float* x, const void* h, int32_t h_
 SVAE_API int svae_dropout_branch_grad(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
                              uint64_t offset, void* stream);
 
-/* Decoding step glue: x (fp32 residual stream, updated in place) += h, then y = LayerNorm(x) with the arithmetic of
- * svae_layernorm_fwd (reference core/transformer_layer.py:35-61: `x = x + h` followed by the next sub-layer's norm). */
-SVAE_API int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
-                            int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, void* stream);
+/* x_out = x + h (fp32 stream + branch), then y = LayerNorm(x_out) with the arithmetic of svae_layernorm_fwd (reference
+ * core/transformer_layer.py:35-61: `x = x + h` followed by the next sub-layer's norm).  x_out == x updates the stream
+ * in place (token-by-token decoding); training passes a new buffer and mean / rstd [rows] for the backward pass. */
+SVAE_API int svae_residual_layernorm(const float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
+                            int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, float* x_out, float* mean,
+                            float* rstd, void* stream);
 
 /* One-launch restatement of GenerationState.process_logits with its default settings (reference
  * core/generation.py:40-72): repetition penalty over the last `penalty_window` generated tokens, temperature, nucleus

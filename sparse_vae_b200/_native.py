@@ -115,7 +115,7 @@ def _load() -> C.CDLL:
     lib.svae_layernorm_bwd_workspace_floats.restype = i64
     lib.svae_layernorm_bwd_workspace_floats.argtypes = [i64, i32]
     lib.svae_layernorm_bwd.restype = C.c_int
-    lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, i64, vp]
+    lib.svae_layernorm_bwd.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.svae_vocab_ce_supported.restype = C.c_int
     lib.svae_vocab_ce_supported.argtypes = [i32]
     lib.svae_vocab_ce.restype = C.c_int
@@ -139,7 +139,7 @@ def _load() -> C.CDLL:
     lib.svae_residual_add.restype = C.c_int
     lib.svae_residual_add.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.svae_residual_layernorm.restype = C.c_int
-    lib.svae_residual_layernorm.argtypes = [vp, vp, i32, vp, vp, i64, i32, C.c_float, vp, i32, vp]
+    lib.svae_residual_layernorm.argtypes = [vp, vp, i32, vp, vp, i64, i32, C.c_float, vp, i32, vp, vp, vp, vp]
     lib.svae_sample_top_p_supported.restype = C.c_int
     lib.svae_sample_top_p_supported.argtypes = [i32, i32]
     lib.svae_sample_top_p.restype = C.c_int

@@ -264,6 +264,9 @@ class TransformerLayer(nn.Module):
         else:
             h = self.attn_layer_norm(x)
         h = self.attention(h, h, h, padding=padding)
+        if x.shape == h.shape and not (self.cross_attention and context is not None):
+            x, h = self.ffn_layer_norm.add_fork(x, h)        # x = x + h and the feed-forward norm, one launch
+            return residual_dropout_add(x, self.ffn(h), self.dropout)
         x = residual_add(x, h) if x.shape == h.shape else h  # learned queries change the length: no residual
 
         if self.cross_attention and context is not None:

@@ -133,7 +133,8 @@ class GraphedDecoder:
         y = torch.empty_like(h)
         N.check(N.lib.svae_residual_layernorm(x.data_ptr(), h.data_ptr(), N.svae_dtype(h.dtype), norm.weight.data_ptr(),
                                               N.ptr(norm.bias), x.numel() // n, n, float(norm.eps), y.data_ptr(),
-                                              N.svae_dtype(h.dtype), N.current_stream(x.device)), 'svae_residual_layernorm')
+                                              N.svae_dtype(h.dtype), x.data_ptr(), None, None,
+                                              N.current_stream(x.device)), 'svae_residual_layernorm')
         return y
 
     def _process_logits(self, logits: Tensor) -> Tensor:

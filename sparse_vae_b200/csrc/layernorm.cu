@@ -105,11 +105,13 @@ layernorm_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ gamma, 
 
 // Token-by-token decoding (core/decode.py): the residual stream update and the next LayerNorm in one pass.
 // x (fp32, in place) += h; y = LayerNorm(x).  Same arithmetic as the separate `x + h` (fp32 add of the promoted
-// 16-bit branch output) followed by layernorm_fwd_kernel; no statistics are kept (inference only).
+// 16-bit branch output) followed by layernorm_fwd_kernel.  x_out may be x itself (decoding) or a new buffer (training,
+// where the old x is still needed by the backward pass of the norm it fed); mean / rstd are written when given.
 template <typename TH, typename TY, int VPT>
 __global__ void __launch_bounds__(kLnThreads)
-residual_layernorm_kernel(float* __restrict__ x, const TH* __restrict__ h, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, TY* __restrict__ y, int64_t rows, float eps) {
+residual_layernorm_kernel(const float* x, const TH* __restrict__ h, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, TY* __restrict__ y, float* x_out, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, int64_t rows, float eps) {
   constexpr int N = 128 * VPT;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -124,7 +126,7 @@ residual_layernorm_kernel(float* __restrict__ x, const TH* __restrict__ h, const
       Vec4<TH>::load(h + r * N + (i * 32 + lane) * 4, hv);
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[i][e] += hv[e];
-      Vec4<float>::store(x + r * N + (i * 32 + lane) * 4, v[i]);
+      Vec4<float>::store(x_out + r * N + (i * 32 + lane) * 4, v[i]);
       s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
     const float mean = warp_sum(s) * (1.0f / N);
@@ -144,6 +146,7 @@ residual_layernorm_kernel(float* __restrict__ x, const TH* __restrict__ h, const
       for (int e = 0; e < 4; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, g[e], bt[e]);
       Vec4<TY>::store(y + r * N + (i * 32 + lane) * 4, o);
     }
+    if (mean_out && lane == 0) { mean_out[r] = mean; rstd_out[r] = rstd; }
   }
 }
 
@@ -152,7 +155,7 @@ template <typename TX, typename TY, int VPT>
 __global__ void __launch_bounds__(kLnThreads)
 layernorm_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, TX* __restrict__ dx,
-                     const TX* __restrict__ dres, float* __restrict__ partial, int64_t rows) {
+                     const TX* __restrict__ dres, TY* __restrict__ dx_low, float* __restrict__ partial, int64_t rows) {
   constexpr int N = 128 * VPT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + warp;
@@ -197,6 +200,7 @@ layernorm_bwd_kernel(const TY* __restrict__ dy, const TX* __restrict__ x, const 
           for (int e = 0; e < 4; ++e) o[e] += a[e];
         }
         Vec4<TX>::store(dx + r * N + (i * 32 + lane) * 4, o);
+        if (dx_low) Vec4<TY>::store(dx_low + r * N + (i * 32 + lane) * 4, o);     // the same gradient for a 16-bit branch
       }
     }
   }
@@ -263,9 +267,9 @@ static int launch_fwd(int vpt, const void* x, const float* gamma, const float* b
 
 template <typename TX, typename TY>
 static int launch_bwd(int vpt, const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      void* dx, const void* dres, float* partial, int grid, int64_t rows, cudaStream_t st) {
+                      void* dx, const void* dres, void* dx_low, float* partial, int grid, int64_t rows, cudaStream_t st) {
 #define SVAE_LN_BWD(V)                                                                                         \
-  case V: layernorm_bwd_kernel<TX, TY, V><<<grid, kLnThreads, 0, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, (const TX*)dres, partial, rows); break
+  case V: layernorm_bwd_kernel<TX, TY, V><<<grid, kLnThreads, 0, st>>>((const TY*)dy, (const TX*)x, gamma, mean, rstd, (TX*)dx, (const TX*)dres, (TY*)dx_low, partial, rows); break
   switch (vpt) { SVAE_LN_BWD(1); SVAE_LN_BWD(2); SVAE_LN_BWD(4); SVAE_LN_BWD(8); default: return SVAE_ERR_UNSUPPORTED; }
 #undef SVAE_LN_BWD
   SVAE_CUDA_CHECK(cudaGetLastError());
@@ -273,11 +277,11 @@ static int launch_bwd(int vpt, const void* dy, const void* x, const float* gamma
 }
 
 template <typename TH, typename TY>
-static int launch_residual(int vpt, float* x, const void* h, const float* gamma, const float* beta, void* y, int64_t rows,
-                           float eps, cudaStream_t st) {
+static int launch_residual(int vpt, const float* x, const void* h, const float* gamma, const float* beta, void* y,
+                           float* x_out, float* mean, float* rstd, int64_t rows, float eps, cudaStream_t st) {
   const int grid = ln_grid(rows);
 #define SVAE_LN_RES(V)                                                                                         \
-  case V: residual_layernorm_kernel<TH, TY, V><<<grid, kLnThreads, 0, st>>>(x, (const TH*)h, gamma, beta, (TY*)y, rows, eps); break
+  case V: residual_layernorm_kernel<TH, TY, V><<<grid, kLnThreads, 0, st>>>(x, (const TH*)h, gamma, beta, (TY*)y, x_out, mean, rstd, rows, eps); break
   switch (vpt) { SVAE_LN_RES(1); SVAE_LN_RES(2); SVAE_LN_RES(4); SVAE_LN_RES(8); default: return SVAE_ERR_UNSUPPORTED; }
 #undef SVAE_LN_RES
   SVAE_CUDA_CHECK(cudaGetLastError());
@@ -318,7 +322,7 @@ extern "C" int svae_layernorm_fwd(const void* x, int32_t x_dtype, const float* g
 
 extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, int32_t x_dtype, const float* gamma,
                                   const float* mean, const float* rstd, int64_t rows, int32_t n, void* dx,
-                                  const void* dx_residual, float* dgamma, float* dbeta, float* workspace,
+                                  const void* dx_residual, void* dx_low, float* dgamma, float* dbeta, float* workspace,
                                   int64_t workspace_floats, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SVAE_REQUIRE(dy && x && gamma && mean && rstd && workspace && rows >= 0, SVAE_ERR_INVALID, "svae_layernorm_bwd: null argument");
@@ -327,7 +331,7 @@ extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x
   SVAE_REQUIRE(workspace_floats >= (int64_t)grid * 2 * n, SVAE_ERR_INVALID, "svae_layernorm_bwd: workspace too small");
   ScopedKernelTimer timer("layernorm_bwd", st);
   auto run = [&]() -> int {
-    SVAE_LN_DISPATCH(launch_bwd, n / 128, dy, x, gamma, mean, rstd, dx, dx_residual, workspace, grid, rows, st);
+    SVAE_LN_DISPATCH(launch_bwd, n / 128, dy, x, gamma, mean, rstd, dx, dx_residual, dx_low, workspace, grid, rows, st);
     SVAE_REQUIRE(false, SVAE_ERR_UNSUPPORTED, "svae_layernorm_bwd: dtype pair (%d -> %d) not supported", x_dtype, y_dtype);
   };
   int rc = run();
@@ -339,16 +343,20 @@ extern "C" int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x
   return SVAE_OK;
 }
 
-extern "C" int svae_residual_layernorm(float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
-                                       int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, void* stream) {
+extern "C" int svae_residual_layernorm(const float* x, const void* h, int32_t h_dtype, const float* gamma, const float* beta,
+                                       int64_t rows, int32_t n, float eps, void* y, int32_t y_dtype, float* x_out, float* mean,
+                                       float* rstd, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  SVAE_REQUIRE(x && h && gamma && y && rows >= 0, SVAE_ERR_INVALID, "svae_residual_layernorm: null argument");
+  SVAE_REQUIRE(x && h && gamma && y && x_out && rows >= 0, SVAE_ERR_INVALID, "svae_residual_layernorm: null argument");
+  SVAE_REQUIRE((mean == nullptr) == (rstd == nullptr), SVAE_ERR_INVALID, "svae_residual_layernorm: mean and rstd go together");
   SVAE_REQUIRE(ln_shape_ok(n), SVAE_ERR_UNSUPPORTED, "svae_residual_layernorm: width %d not in {128, 256, 512, 1024}", n);
   SVAE_REQUIRE(h_dtype == y_dtype && (h_dtype == SVAE_DTYPE_F16 || h_dtype == SVAE_DTYPE_BF16 || h_dtype == SVAE_DTYPE_F32),
                SVAE_ERR_UNSUPPORTED, "svae_residual_layernorm: branch and output must share one dtype (%d, %d)", h_dtype, y_dtype);
   if (rows == 0) return SVAE_OK;
   ScopedKernelTimer timer("residual_layernorm", st);
-  if (h_dtype == SVAE_DTYPE_F16) return launch_residual<__half, __half>(n / 128, x, h, gamma, beta, y, rows, eps, st);
-  if (h_dtype == SVAE_DTYPE_BF16) return launch_residual<__nv_bfloat16, __nv_bfloat16>(n / 128, x, h, gamma, beta, y, rows, eps, st);
-  return launch_residual<float, float>(n / 128, x, h, gamma, beta, y, rows, eps, st);
+  if (h_dtype == SVAE_DTYPE_F16)
+    return launch_residual<__half, __half>(n / 128, x, h, gamma, beta, y, x_out, mean, rstd, rows, eps, st);
+  if (h_dtype == SVAE_DTYPE_BF16)
+    return launch_residual<__nv_bfloat16, __nv_bfloat16>(n / 128, x, h, gamma, beta, y, x_out, mean, rstd, rows, eps, st);
+  return launch_residual<float, float>(n / 128, x, h, gamma, beta, y, x_out, mean, rstd, rows, eps, st);
 }

@@ -306,5 +306,5 @@ def test_residual_layernorm_equals_add_then_layernorm(dtype, rows, n):
     y = torch.empty_like(h)
     N.check(N.lib.svae_residual_layernorm(x.data_ptr(), h.data_ptr(), N.svae_dtype(dtype), norm.weight.data_ptr(),
                                           norm.bias.data_ptr(), rows, n, norm.eps, y.data_ptr(), N.svae_dtype(dtype),
-                                          N.current_stream(dev)), 'svae_residual_layernorm')
+                                          x.data_ptr(), None, None, N.current_stream(dev)), 'svae_residual_layernorm')
     assert torch.equal(x, want_x) and want_y.dtype == dtype and torch.equal(y, want_y)

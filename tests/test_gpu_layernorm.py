@@ -118,3 +118,42 @@ def test_norm_fork_matches_separate_norm_and_skip(autocast):
     a, b = run(True), run(False)
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
     assert (a[1] - b[1]).abs().max().item() <= 1e-6 * b[1].abs().max().item()
+
+
+def test_add_fork_matches_residual_add_then_norm():
+    """(x + h, LN(x + h)) in one launch, backward with the skip gradient and the 16-bit branch gradient from the same
+    LayerNorm-backward pass == residual_add + LayerNorm + autograd's accumulation and cast."""
+    from sparse_vae_b200.core.layer_norm import LayerNorm, _AddNormFn
+    from sparse_vae_b200.core.residual import residual_add
+    dev = torch.device('cuda')
+    torch.manual_seed(8)
+    ln = LayerNorm(512).to(dev)
+    with torch.no_grad():
+        ln.weight.normal_(1, 0.1)
+        ln.bias.normal_(0, 0.1)
+    x = torch.randn(5, 257, 512, device=dev, requires_grad=True)
+    h = torch.randn(5, 257, 512, device=dev).to(torch.bfloat16).requires_grad_()
+    w = torch.randn(512, 512, device=dev, dtype=torch.bfloat16) * 0.05
+    g = torch.randn(5, 257, 512, device=dev)
+
+    def run(fused):
+        x.grad = h.grad = None
+        ln.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            if fused:
+                s, y = ln.add_fork(x, h)
+                assert isinstance(y.grad_fn, _AddNormFn._backward_cls)
+            else:
+                s = residual_add(x, h)
+                y = ln(s)
+            out = s + (y @ w).float()
+        out.backward(g)
+        return out.detach().clone(), x.grad.clone(), h.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert (a[1] - b[1]).abs().max().item() <= 1e-6 * b[1].abs().max().item()
+    assert a[2].dtype == torch.bfloat16
+    flips = (a[2] != b[2])
+    assert flips.float().mean().item() <= 1e-3                              # last-bit dx differences at a rounding boundary
+    assert ((a[2].float() - b[2].float()).abs() <= b[2].float().abs() * 2 ** -7 + 1e-12).all()
