@@ -113,3 +113,40 @@ def test_replace_first_position_matches_cat_and_gradients():
     (out * w).sum().backward()
     (ref * w).sum().backward()
     assert torch.equal(base.grad, base2.grad) and torch.equal(row.grad, row2.grad)
+
+
+# ---------------------------------------------------------------- graphed decoding: static restatement of process_logits
+@pytest.mark.parametrize('kwargs', [dict(), dict(temperature=0.0), dict(top_k=5), dict(top_p=1.0), dict(repetition_penalty=1.0),
+                                    dict(top_k=7, top_p=0.5, temperature=0.7)])
+def test_static_process_logits_equals_generation_state(kwargs):
+    """core/decode.py restates GenerationState.process_logits with fixed shapes (device-side column counter, clamped
+    penalty window).  On the CPU both run on the same logits with the same generator state: identical tokens."""
+    import types
+
+    from sparse_vae_b200.core import decode
+    from sparse_vae_b200.core.generation import GenerationState
+
+    torch.manual_seed(0)
+    B, V, max_len = 5, 512, 700
+    state = GenerationState(max_len, B, 1, 2, device=torch.device('cpu'), **kwargs)
+    shadow = GenerationState(max_len, B, 1, 2, device=torch.device('cpu'), **kwargs)
+    for step in range(1, 600):
+        logits = torch.randn(B, V) * 3
+        logits[:, 2] = -50.0                          # never the end token: the live batch stays complete
+        if step in (3, 40, 599):                      # compare at a short, a medium and a > 512-token history
+            dec = types.SimpleNamespace(state=shadow, ids=shadow.output_ids, column=torch.tensor([[shadow.current_index]]),
+                                        window_offsets=torch.arange(-decode.PENALTY_WINDOW, 0)[None])
+            rng = torch.get_rng_state()
+            want_logits = logits.clone()
+            state.process_logits(want_logits)
+            want = state.output_ids[:, state.current_index - 1].clone()
+            torch.set_rng_state(rng)
+            got = decode.GraphedDecoder._process_logits(dec, logits.clone())
+            assert torch.equal(got, want), (step, got, want)
+            shadow.output_ids[:, shadow.current_index] = got
+            shadow.current_index += 1
+        else:                                         # fill the history with arbitrary (never end) tokens
+            tok = torch.randint(3, V, (B,))
+            for s in (state, shadow):
+                s.output_ids[:, s.current_index] = tok
+                s.current_index += 1
