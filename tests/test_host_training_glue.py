@@ -150,3 +150,43 @@ def test_static_process_logits_equals_generation_state(kwargs):
             for s in (state, shadow):
                 s.output_ids[:, s.current_index] = tok
                 s.current_index += 1
+
+
+# ---------------------------------------------------------------- graphed decoding: ring KV cache vs the layout oracle
+def _ring_slot(p, block, window):
+    return p if p < block else block + (p - block) % (window * block)
+
+
+def _slot_position(slot, pos, block, window):
+    """Python statement of csrc/decode_attn.cu::slot_position."""
+    if slot < block:
+        return slot if slot <= pos else -1
+    if pos < block:
+        return -1
+    ring = window * block
+    q = block + (pos - block) - ((pos - block) - (slot - block)) % ring
+    if q < block:
+        return -1
+    first_block = max(1, pos // block - (window - 1))
+    return q if q >= first_block * block else -1
+
+
+@pytest.mark.parametrize('window', [1, 2, 4, 7])
+def test_ring_cache_shows_exactly_the_keys_of_the_layout_row(window):
+    """Decoding position p must see the keys that row p's block of the causal include_cls layout allows (and, inside the
+    diagonal block, only keys <= p): the ring cache of decode_attn_kernel holds exactly those, each in one slot."""
+    from oracle import layout as olayout
+    block, cache = 32, (window + 1) * 32
+    length = 32 * 14
+    lay = olayout.layout_2d(length // block, window, causal=True, include_cls=True)
+    stored = {}                                            # slot -> position last written there
+    for p in range(length):
+        stored[_ring_slot(p, block, window)] = p
+        visible = {}
+        for slot in range(cache):
+            q = _slot_position(slot, p, block, window)
+            if q >= 0:
+                assert stored.get(slot) == q, (p, slot, q, stored.get(slot))      # the slot really holds that position
+                visible[q] = slot
+        want = {q for q in range(p + 1) if lay[p // block, q // block]}
+        assert set(visible) == want, (p, sorted(set(visible) ^ want)[:8])
