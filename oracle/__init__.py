@@ -9,6 +9,7 @@ algorithm for the path named in BASELINE.json `north_star`:
   * latent bottleneck + Philox    -> oracle/bottleneck.py  (reference core/conditional_gaussian.py:18-30,
                                                             core/continuous_autoencoder.py:42-52, torch Normal.rsample)
   * whole TransformerVAE step     -> oracle/model.py       (reference transformer_vae.py:42-93 and callees)
+  * token-by-token decoding       -> oracle/decoding.py    (reference core/generation.py:40-72, core/attention.py:107-142)
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
 leg may import it, and only as the checker.  Nothing under `sparse_vae_b200/` imports it; the

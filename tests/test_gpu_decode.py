@@ -11,6 +11,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).parent))
 sys.path.insert(0, str(Path(__file__).parent / 'golden'))
 import make_golden as mg  # noqa: E402
+from oracle import decoding as odec  # noqa: E402
 from util import oracle_attention, rel_err  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -189,30 +190,6 @@ def _run_sampler(logits, uniforms, ids=None, column=1, alive=None, penalty=1.0, 
     return ids, alive, int(finished.item())
 
 
-def _nucleus_weights(x64, top_p):
-    """The kernel's rule in float64 on the CPU: keep the most likely values while their mass stays <= top_p, admit
-    boundary ties in index order while they fit, never keep nothing.  x64: [V] float64 (exactly representable logits)."""
-    e = torch.exp(x64 - x64.max())
-    budget = top_p * e.sum()
-    keep = torch.zeros_like(e, dtype=torch.bool)
-    tail = 0.0
-    for value in torch.unique(x64).flip(0).tolist():
-        group = x64 == value
-        mass = e[group].sum().item()
-        if tail + mass <= budget:
-            keep |= group
-            tail += mass
-            continue
-        each = e[group][0].item()
-        n = int((budget.item() - tail) // each)
-        if tail == 0.0:
-            n = max(n, 1)
-        idx = group.nonzero().flatten()[:n]
-        keep[idx] = True
-        break
-    return torch.where(keep, e, torch.zeros_like(e))
-
-
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize('V,top_p,spread', [(4096, 0.9, 3.0), (8192, 0.5, 1.0), (1000, 0.97, 6.0), (4096, 1.0, 2.0)])
 def test_sampler_draws_the_inverse_cdf_token_of_the_reference_nucleus(dtype, V, top_p, spread):
@@ -225,19 +202,13 @@ def test_sampler_draws_the_inverse_cdf_token_of_the_reference_nucleus(dtype, V, 
     uniforms = torch.rand(B, generator=g).to(dev)
     ids, _, _ = _run_sampler(logits, uniforms, top_p=top_p, end_token=-1)
     got = ids[:, 1].cpu()
-    w = _nucleus_weights(row.double(), top_p)
+    w = odec.nucleus_weights(row.double(), top_p)
     # the reference's own rule (sort, softmax, cumsum > top_p masked, first kept) keeps the same set up to boundary ties
-    sorted_x, order = row.float().sort(descending=True)
-    probs = sorted_x.softmax(-1)
-    tail = probs.cumsum(-1) > top_p
-    tail[0] = False
-    ref_keep = torch.zeros(V, dtype=torch.bool)
-    ref_keep[order[~tail]] = True
+    ref_keep = odec.nucleus_keep_reference(row, top_p)
     boundary = row.float()[w > 0].min()
     differs = (ref_keep != (w > 0))
     assert (row.float()[differs] == boundary).all() and differs.sum() <= 2 + (row.float() == boundary).sum()
-    cdf = w.cumsum(0)
-    want = torch.searchsorted(cdf, uniforms.cpu().double() * cdf[-1], right=True).clamp_(max=V - 1)
+    want = odec.inverse_cdf_token(w, uniforms.cpu())
     mismatch = (got != want)
     assert mismatch.float().mean() <= 0.005, (got[mismatch][:8], want[mismatch][:8])
     assert (w[got] > 0).all()                      # never a token outside the nucleus
@@ -253,7 +224,7 @@ def test_sampler_full_vocab_frequencies():
     uniforms = torch.rand(B, generator=g).to(dev)
     ids, _, _ = _run_sampler(logits, uniforms, top_p=0.9, end_token=-1)
     got = ids[:, 1].cpu()
-    w = _nucleus_weights(row.double(), 0.9)
+    w = odec.nucleus_weights(row.double(), 0.9)
     p = w / w.sum()
     assert (w[got] > 0).all()
     counts = torch.bincount(got, minlength=V).double()

@@ -175,10 +175,9 @@ def _slot_position(slot, pos, block, window):
 def test_ring_cache_shows_exactly_the_keys_of_the_layout_row(window):
     """Decoding position p must see the keys that row p's block of the causal include_cls layout allows (and, inside the
     diagonal block, only keys <= p): the ring cache of decode_attn_kernel holds exactly those, each in one slot."""
-    from oracle import layout as olayout
+    from oracle import decoding as odec
     block, cache = 32, (window + 1) * 32
     length = 32 * 14
-    lay = olayout.layout_2d(length // block, window, causal=True, include_cls=True)
     stored = {}                                            # slot -> position last written there
     for p in range(length):
         stored[_ring_slot(p, block, window)] = p
@@ -188,5 +187,5 @@ def test_ring_cache_shows_exactly_the_keys_of_the_layout_row(window):
             if q >= 0:
                 assert stored.get(slot) == q, (p, slot, q, stored.get(slot))      # the slot really holds that position
                 visible[q] = slot
-        want = {q for q in range(p + 1) if lay[p // block, q // block]}
+        want = odec.visible_positions(p, window, block)
         assert set(visible) == want, (p, sorted(set(visible) ^ want)[:8])

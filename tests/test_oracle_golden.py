@@ -146,3 +146,25 @@ def test_model_oracle_matches_reference_training_step(golden_dir):
     for key in g.files:
         if key.startswith('grad.'):
             np.testing.assert_allclose(params[key[5:]].grad.numpy(), g[key], rtol=2e-3, atol=2e-7)
+
+
+def test_decoding_oracle_nucleus_rules_agree():
+    """oracle/decoding.py: the sort-free statement of the nucleus keeps the set of the reference's own rule
+    (core/generation.py:55-62) up to tokens tying at the boundary value."""
+    import torch
+
+    from oracle import decoding as odec
+    g = torch.Generator().manual_seed(3)
+    for V, top_p, spread in [(4096, 0.9, 3.0), (1000, 0.97, 6.0), (512, 0.3, 1.0), (4096, 1.0, 2.0)]:
+        row = (torch.randn(V, generator=g) * spread).to(torch.float16)
+        w = odec.nucleus_weights(row.double(), top_p)
+        ref = odec.nucleus_keep_reference(row, top_p)
+        kept = w > 0
+        assert kept.any()
+        boundary = row.float()[kept].min()
+        differs = ref != kept
+        assert (row.float()[differs] == boundary).all()
+        # inverse CDF: u = 0 picks the first kept token, u -> 1 the last
+        first, last = kept.nonzero()[0].item(), kept.nonzero()[-1].item()
+        got = odec.inverse_cdf_token(w, torch.tensor([0.0, 1.0 - 1e-12, 1.0], dtype=torch.float64))
+        assert got.tolist() == [first, last, last]
