@@ -32,39 +32,42 @@ class GenerationState:
         return self.output_ids[self.live_sample_mask, self.current_index - 1, None]
 
     def process_logits(self, logits: Tensor):
-        ids = None
+        """Turns the live samples' next-token logits into tokens, appends them and returns which samples go on."""
         if self.repetition_penalty > 1.0:
-            start = max(self.current_index - 512, 0)
-            seen = self.output_ids[self.live_sample_mask, start:self.current_index]
-            seen_logits = logits.gather(dim=-1, index=seen)
-            seen_logits = torch.where(seen_logits < 0.0, seen_logits * self.repetition_penalty,
-                                      seen_logits / self.repetition_penalty)
-            logits.scatter_(dim=-1, index=seen, src=seen_logits)
+            self._penalise_repeats(logits)
+        greedy = self.temperature <= 0.0 or self.top_k == 1
+        tokens = (logits.argmax(dim=-1) if greedy else self._draw(logits / self.temperature)).flatten()
 
-        if self.temperature <= 0.0 or self.top_k == 1:          # greedy
-            logits, ids = logits.max(dim=-1, keepdim=True)
-        else:
-            logits = logits / self.temperature
-            if self.top_k > 0:
-                logits, ids = logits.topk(k=max(self.top_k, 1), sorted=False)
-            if self.top_p < 1.0:                                # nucleus: drop the tail beyond cumulative mass top_p
-                logits, order = logits.sort(descending=True)
-                ids = order if ids is None else ids.gather(dim=-1, index=order)
-                probs = logits.softmax(dim=-1)
-                tail = probs.cumsum(dim=-1) > self.top_p
-                tail[..., :1] = False
-                probs[tail] = 0.0
-            else:
-                probs = logits.softmax(dim=-1)
-            picked = probs.multinomial(num_samples=1).view(*logits.shape[:-1], 1)
-            ids = picked if ids is None else ids.gather(dim=-1, index=picked)
-
-        ids = ids.flatten()
-        self.output_ids[self.live_sample_mask, self.current_index] = ids.type_as(self.output_ids)
+        self.output_ids[self.live_sample_mask, self.current_index] = tokens.type_as(self.output_ids)
         self.current_index += 1
-        continuing = (ids != self.end_token) & (self.current_index < self.output_ids.shape[-1])
+        continuing = (tokens != self.end_token) & (self.current_index < self.output_ids.shape[-1])
         self.live_sample_mask[self.live_sample_mask.clone()] &= continuing
         return continuing
+
+    def _penalise_repeats(self, logits: Tensor):
+        """Tokens generated in the last 512 steps become less likely: positive logits divided, negative multiplied."""
+        first = max(self.current_index - 512, 0)
+        recent = self.output_ids[self.live_sample_mask, first:self.current_index]
+        values = logits.gather(dim=-1, index=recent)
+        values = torch.where(values < 0.0, values * self.repetition_penalty, values / self.repetition_penalty)
+        logits.scatter_(dim=-1, index=recent, src=values)
+
+    def _draw(self, logits: Tensor) -> Tensor:
+        """top-k, then nucleus filtering on the sorted distribution, then one multinomial draw per sample."""
+        candidates = None                                   # token ids of the columns of `logits`, None = identity
+        if self.top_k > 0:
+            logits, candidates = logits.topk(k=max(self.top_k, 1), sorted=False)
+        if self.top_p < 1.0:
+            logits, order = logits.sort(descending=True)
+            candidates = order if candidates is None else candidates.gather(dim=-1, index=order)
+            probs = logits.softmax(dim=-1)
+            beyond = probs.cumsum(dim=-1) > self.top_p      # cumulative mass already past top_p: dropped ...
+            beyond[..., :1] = False                         # ... except the most likely token
+            probs[beyond] = 0.0
+        else:
+            probs = logits.softmax(dim=-1)
+        column = probs.multinomial(num_samples=1).view(*logits.shape[:-1], 1)
+        return column if candidates is None else candidates.gather(dim=-1, index=column)
 
     def should_stop(self) -> bool:
         return self.current_index >= self.output_ids.shape[-1] - 1 or not self.live_sample_mask.any()
