@@ -53,7 +53,8 @@ extern "C" {
 
 /* svae_attn_desc.flags */
 #define SVAE_ATTN_FORCE_EXACT  1   /* run 16-bit inputs through the exact CUDA-core path (cross-check / debugging) */
-#define SVAE_ATTN_PERSISTENT   2   /* forward: use the persistent warp-specialised kernel (experimental; default = one CTA per tile) */
+#define SVAE_ATTN_PERSISTENT   2   /* forward: persistent warp-specialised kernel (what the host wrapper selects for <= 8 key slots;
+                                      without the flag: one CTA per tile, also used for wider windows and score dumps) */
 
 /* Block-sparse attention problem.  Tensors are [batch, heads, seq_len, head_dim] with arbitrary
  * batch/head/row strides (in ELEMENTS) and unit inner stride -- the reference hands the op strided
@@ -100,6 +101,13 @@ SVAE_API int svae_layout_build(int32_t num_blocks, int32_t window_size, int32_t 
 SVAE_API int svae_attn_fwd(const svae_attn_desc* desc, const void* q, const void* k, const void* v,
                   const float* key_padding_mask, void* out, float* lse, void* stream);
 
+/* Which kernels svae_attn_bwd will run for this problem: the tcgen05 kernels need 16-bit tensors, head_dim 64 and
+ * a band of <= 13 key blocks; everything else takes the exact CUDA-core kernels (20-40x slower; the host wrapper
+ * warns when 16-bit tensors end up there).  < 0: invalid descriptor. */
+#define SVAE_BWD_PATH_TCGEN05 0
+#define SVAE_BWD_PATH_EXACT   1
+SVAE_API int svae_attn_bwd_path(const svae_attn_desc* desc);
+
 SVAE_API size_t svae_attn_bwd_workspace_bytes(const svae_attn_desc* desc);
 /* dq, dk, dv (same dtype as q) from dout; workspace: device scratch of at least
  * svae_attn_bwd_workspace_bytes(desc) bytes, 256-byte aligned, contents ignored on entry. */
@@ -107,7 +115,7 @@ SVAE_API int svae_attn_bwd(const svae_attn_desc* desc, const void* q, const void
                   const void* out, const void* dout, const float* lse, const float* key_padding_mask,
                   void* dq, void* dk, void* dv, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Debug variant of svae_attn_fwd for the tcgen05 path.  s_dump (may be NULL): raw scores S = q k^T (before
+/* Test hook (no global state): variant of svae_attn_fwd for the tcgen05 path.  s_dump (may be NULL): raw scores S = q k^T (before
  * scale/masks) of every query row against its tile's key slots, [batch, heads, seq_len, slots*32] fp32
  * (slots = svae_attn_fwd_slots(desc)).  timeline (may be NULL): int64 [num_ctas, 5, 8] per-warp clock64
  * stamps of the kernel's phases (CTA order: batch, head, tile). */
@@ -116,18 +124,6 @@ SVAE_API int svae_attn_fwd_debug(const svae_attn_desc* desc, const void* q, cons
                         const float* key_padding_mask, void* out, float* lse, float* s_dump,
                         long long* timeline, void* stream);
 
-/* Debug: when non-NULL, the next svae_attn_bwd launches (tcgen05 path) write clock64 phase stamps into
- * timeline, int64 [2 kernels (dQ pass, dK/dV pass)][num_ctas][3 roles: warp 0, warp 3, MMA warp][16].  Process-global. */
-SVAE_API void svae_debug_set_bwd_timeline(long long* timeline);
-
-/* Debug micro-benchmark (one CTA): clock64 cycles to issue `count` back-to-back tcgen05.mma (M=128, K=16, N=n).
- * variant bit 0: A from TMEM, bit 1: B MN-major, bit 2: two issuing warps.  out: int64[4] =
- * {issue, issue+drain} per issuing warp. */
-SVAE_API int svae_debug_mma_bench(int variant, int n, int count, long long* out, void* stream);
-/* Debug micro-benchmark (one CTA, `warps` warps): cycles per warp for `iters` x 8 back-to-back instructions of
- * mode 0 MUFU.EX2, 1 F2FP bf16x2 pack, 2 FFMA, 3 FMNMX3, 4 tcgen05.ld 32x32b.x32, 5 tcgen05.st 32x32b.x16,
- * 6 the softmax step (FFMA, EX2, FADD, pack).  out: int64[64]. */
-SVAE_API int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out, void* stream);
 
 /* ---- latent bottleneck ---------------------------------------------------------------------- */
 #define SVAE_BOTTLENECK_WORKSPACE_BYTES 8448

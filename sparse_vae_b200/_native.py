@@ -32,7 +32,7 @@ EXPORTS = (
     'svae_abi_version', 'svae_last_error', 'svae_device_check', 'svae_layout_nnz', 'svae_layout_build',
     'svae_attn_fwd', 'svae_attn_bwd_workspace_bytes', 'svae_attn_bwd', 'svae_attn_fwd_slots', 'svae_attn_fwd_debug',
     'svae_bottleneck_fwd', 'svae_bottleneck_philox_increment', 'svae_bottleneck_bwd',
-    'svae_profile_begin', 'svae_profile_end', 'svae_debug_mma_bench', 'svae_debug_pipe_bench', 'svae_debug_set_bwd_timeline',
+    'svae_profile_begin', 'svae_profile_end', 'svae_attn_bwd_path',
     'svae_multi_tensor_chunks', 'svae_multi_tensor_scale_copy', 'svae_clip_grad_norm', 'svae_radam_step',
     'svae_vocab_ce_supported', 'svae_vocab_ce', 'svae_rotary', 'svae_colsum_workspace_floats', 'svae_colsum_counters', 'svae_colsum',
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
@@ -96,8 +96,8 @@ def _load() -> C.CDLL:
     lib.svae_profile_begin.argtypes = []
     lib.svae_profile_end.restype = C.c_int
     lib.svae_profile_end.argtypes = [C.c_char_p, C.c_size_t]
-    lib.svae_debug_mma_bench.restype = C.c_int
-    lib.svae_debug_mma_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.svae_attn_bwd_path.restype = C.c_int
+    lib.svae_attn_bwd_path.argtypes = [desc_p]
     lib.svae_multi_tensor_chunks.restype = i64
     lib.svae_multi_tensor_chunks.argtypes = [i32, vp]
     lib.svae_multi_tensor_scale_copy.restype = C.c_int
@@ -144,16 +144,25 @@ def _load() -> C.CDLL:
     lib.svae_sample_top_p_supported.argtypes = [i32, i32]
     lib.svae_sample_top_p.restype = C.c_int
     lib.svae_sample_top_p.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, i64, vp]
-    lib.svae_debug_set_bwd_timeline.restype = None
-    lib.svae_debug_set_bwd_timeline.argtypes = [vp]
-    lib.svae_debug_pipe_bench.restype = C.c_int
-    lib.svae_debug_pipe_bench.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     if lib.svae_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI version {lib.svae_abi_version()} != expected {ABI_VERSION}; rebuild")
     return lib
 
 
 lib = _load()
+
+
+def load_debug() -> C.CDLL:
+    """libsvae_b200_dbg.so (include/sparse_vae_b200_debug.h): micro-benchmarks, never loaded by the product path."""
+    path = _HERE / 'csrc' / 'libsvae_b200_dbg.so'
+    if not path.exists():
+        raise ImportError(f"{path} is missing: build it with `python sparse_vae_b200/csrc/build.py --debug`")
+    dbg = C.CDLL(str(path))
+    for name in ('svae_debug_mma_bench', 'svae_debug_pipe_bench'):
+        fn = getattr(dbg, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return dbg
 
 
 def check(rc: int, what: str):

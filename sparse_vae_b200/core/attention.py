@@ -160,7 +160,9 @@ class Attention(nn.Module):
             # Dense attention of the Perceiver encoder (64 learned queries over the whole sequence) and of non-sparse
             # decoders: same arithmetic -- softmax(q k^T / sqrt(d) - 1e7 * mask) v -- through the library's fused
             # kernel, which reads the strided head views directly (the explicit form copies k^T and v per call).
-            bias = None if padding is None else (padding[:, None, None, :] * -1e7).to(q.dtype)    # autocast casts it along
+            # the reference subtracts a float32 1e7 from promoted scores; in fp16 that constant would become -inf and a
+            # fully padded row NaN, so the bias is clamped to the dtype's finite range before the cast
+            bias = None if padding is None else (padding[:, None, None, :] * -1e7).clamp_min(torch.finfo(q.dtype).min).to(q.dtype)
             out = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, is_causal=self.causal and bias is None)
         else:
             scores = q @ k.transpose(-1, -2) * k.shape[-1] ** -0.5

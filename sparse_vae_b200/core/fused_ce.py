@@ -72,6 +72,13 @@ class _VocabNLL(torch.autograd.Function):
         b_c = bias.to(compute_dtype) if bias is not None else None
         lab = labels.reshape(-1).contiguous()
         tw = token_w.reshape(-1).to(torch.float32).contiguous()
+        # fp16 compute (the reference's default precision): the per-token weights are ~1/valid_tokens (2e-5 at 65k
+        # tokens), so w_r * (softmax - onehot) would flush most of the softmax tail to zero when it is rounded to
+        # fp16 -- BEFORE any GradScaler factor arrives with the upstream gradient in backward.  The gradients built in
+        # forward therefore carry an exact power-of-two factor (the largest one <= the row count, a host-side bound
+        # on the valid tokens: no device sync) that backward divides out again in fp32.
+        gscale = float(2 ** (max(rows, 1).bit_length() - 1)) if compute_dtype == torch.float16 else 1.0
+        tw_kernel = tw * gscale if gscale != 1.0 else tw
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]]
         any_grad = any(need)
         nll = torch.empty(rows, device=h.device, dtype=torch.float32)
@@ -94,7 +101,7 @@ class _VocabNLL(torch.autograd.Function):
             r1 = min(rows, r0 + row_chunk)
             logits = F.linear(h[r0:r1], w_c, b_c)                          # library GEMM (cuBLAS), [rc, V]
             N.check(N.lib.svae_vocab_ce(logits.data_ptr(), dt, r1 - r0, V, logits.stride(0), lab[r0:r1].data_ptr(),
-                                        tw[r0:r1].data_ptr(), nll[r0:r1].data_ptr(), int(any_grad), stream), 'svae_vocab_ce')
+                                        tw_kernel[r0:r1].data_ptr(), nll[r0:r1].data_ptr(), int(any_grad), stream), 'svae_vocab_ce')
             if need[0]:
                 torch.mm(logits, w_c, out=dh[r0:r1])
             if need[1] or aug:
@@ -110,6 +117,7 @@ class _VocabNLL(torch.autograd.Function):
         loss = torch.dot(nll, tw)
         ctx.save_for_backward(dh, dw, db)
         ctx.meta = (hidden.shape, hidden.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        ctx.gscale = gscale
         ctx.mark_non_differentiable(nll)
         return loss, nll
 
@@ -117,7 +125,11 @@ class _VocabNLL(torch.autograd.Function):
     def backward(ctx, g: Tensor, _g_nll):
         dh, dw, db = ctx.saved_tensors
         shape, h_dtype, w_dtype, b_dtype = ctx.meta
-        g_h = (dh * g.to(dh.dtype)).to(h_dtype).view(shape) if dh is not None else None
+        if ctx.gscale != 1.0:
+            g = g.float() / ctx.gscale                 # exact: a power of two
+            g_h = (dh.float() * g).to(h_dtype).view(shape) if dh is not None else None
+        else:
+            g_h = (dh * g.to(dh.dtype)).to(h_dtype).view(shape) if dh is not None else None
         g_w = (dw * g).to(w_dtype) if dw is not None else None
         g_b = (db * g).to(b_dtype) if db is not None else None
         return g_h, g_w, g_b, None, None, None, None

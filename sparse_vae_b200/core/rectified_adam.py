@@ -58,7 +58,10 @@ class RAdam(Optimizer):
                 group['step'] += 1
                 continue
 
-            if N.FUSED_EXTRAS and not group['lamb'] and all(p.is_cuda and p.dtype == torch.float32 for p in params):
+            if N.FUSED_EXTRAS and not group['lamb'] and all(
+                    p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+                    and g.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+                    for p, g, a, b in zip(params, grads, m, v)):
                 from ..fused_optim import FusedRAdamStep
                 cache = self.__dict__.setdefault('_fused_steps', {})     # kept off param_groups (state_dict stays clean)
                 fused = cache.get(id(group))

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import warnings
 from dataclasses import dataclass
 from functools import lru_cache
 from typing import ClassVar, Optional
@@ -16,6 +17,9 @@ from typing import ClassVar, Optional
 import torch
 
 from .. import _native as N
+
+
+_WARNED_EXACT = set()
 
 
 def _strides3(t: torch.Tensor):
@@ -82,6 +86,12 @@ class _SparseAttentionFn(torch.autograd.Function):
         desc = _make_desc(cfg, q, k, v, out, ctx.flags)
         desc.do_stride, desc.dq_stride = _strides3(dout), _strides3(dq)
         desc.dk_stride, desc.dv_stride = _strides3(dk), _strides3(dv)
+        if q.dtype != torch.float32 and not (ctx.flags & N.ATTN_FORCE_EXACT) and \
+                N.lib.svae_attn_bwd_path(ctypes.byref(desc)) == 1 and (Dh, cfg.window_size) not in _WARNED_EXACT:
+            _WARNED_EXACT.add((Dh, cfg.window_size))
+            warnings.warn(f"sparse attention backward: {q.dtype} tensors with head_dim {Dh} / window {cfg.window_size} are "
+                          f"outside the tensor-core kernels (head_dim 64, band <= 13 blocks) and run the exact CUDA-core "
+                          f"kernels, 20-40x slower", RuntimeWarning, stacklevel=2)
         ws_bytes = N.lib.svae_attn_bwd_workspace_bytes(ctypes.byref(desc))
         ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=q.device)
         ws_ptr = (ws.data_ptr() + 255) & ~255

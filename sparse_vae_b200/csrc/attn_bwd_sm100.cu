@@ -26,8 +26,6 @@ namespace sm100 {
 
 using namespace ptx;
 
-long long* g_bwd_timeline = nullptr;   // debug only (svae_debug_set_bwd_timeline)
-
 constexpr int kBwdSlots = 8;          // key slots of the default geometry (two CTAs per SM)
 constexpr int kBwdSlotsWide = 14;     // windows 5..10: one CTA per SM
 constexpr int kBwdMathWarps = 8;                 // two warps per TMEM lane quarter: each owns 16 of a slot's 32 columns
@@ -82,11 +80,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const TileGeom g = p.g;
   const int ns = g.nslots;
   const int npass = (ns + PASS - 1) / PASS;
-  long long* tl = nullptr;
-  if (p.timeline && lane == 0 && (warp == 0 || warp == 3 || warp == kBwdMathWarps))
-    tl = p.timeline + ((((int64_t)b * gridDim.y + h) * gridDim.x + t) * 3 + (warp == 0 ? 0 : warp == 3 ? 1 : 2)) * 16;
-  auto stamp = [&](int k) { if (tl) tl[k] = clock64(); };
-  stamp(0);
   const int r0 = 4 * t;
   const int band_lo = r0 - (g.left - 1);
   // SMEM slot order = processing order: band slots 0 .. nband-1, then the global block (slot nband), so that the
@@ -131,7 +124,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  stamp(1);
 
   if (warp == kBwdMathWarps) {
     {   // the whole warp runs the issue path convergently; one lane is elected inside each wrapper
@@ -150,18 +142,14 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                    make_smem_desc(v_addr + koff + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
         }
       };
-
-      stamp(2);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
-      stamp(3);
       issue_s_dp(0);
       tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_ds + c, 0);
         tc_fence_after();
-        if (c < 3) stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {     // dQ += dS_j K_j
           const int j = order(c * PASS + i);
           if (!slot_valid(j)) continue;
@@ -187,7 +175,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
           tc_commit_w(bar_dq);
         }
-        if (c < 3) stamp(5 + 2 * c);
       }
     }
     __syncwarp();
@@ -230,7 +217,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (row_ok && hc == 0) p.delta[stat_idx] = delta;
     const float neg_delta_s = -delta * p.scale;
     const bool has_kpm = bar_red_or(1, kMath, any_kpm);     // also: every thread is done reading sO (-> sG)
-    stamp(2);
 
     auto slot_live = [&](int j) {
       if (r >= g.nb || !slot_valid(j)) return false;
@@ -243,7 +229,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int c = 0; c < npass; ++c) {
       mbar_wait(bar_sdp + c, 0);
       tc_fence_after();
-      if (c < 3) stamp(3 + 2 * c);
       bool wrote_g = false;
       for (int i = 0; i < PASS && c * PASS + i < ns; ++i) {
         const int j = order(c * PASS + i);
@@ -255,11 +240,9 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           tmem_ld16(trow + S::COL_DP + 32 * i + 16 * hc, dv);
           tmem_wait_ld16(sv, dv);
         }
-        if (c == 0 && i == 0) stamp(13);
         // dS of slot i overwrites S columns [16 i, 16 i + 16), which hold scores the PARTNER warp reads: both column
         // halves must have pulled their scores of every slot <= i into registers before either stores
         named_bar_sync(2 + qd, 64);
-        if (c == 0 && i == 0) stamp(14);
         uint32_t dsk[8];
         if (live) {
           uint32_t pk[8];
@@ -306,18 +289,15 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
         }
         tmem_st8(trow + S::COL_S + 16 * i + 8 * hc, dsk);
-        if (c == 0 && i == 0) stamp(15);
       }
       if (wrote_g) fence_proxy_async();        // sG is read by the tensor core through the async proxy
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_ds + c);
-      if (c < 3) stamp(4 + 2 * c);
     }
 
     mbar_wait(bar_dq, 0);
     tc_fence_after();
-    stamp(9);
     {   // this half's 32 of the 64 dQ columns -> 16-bit -> swizzled staging tile (the dO tile is free by now)
       uint32_t v[32];
       tmem_ld32(trow + S::COL_DQ + 32 * hc, v);
@@ -338,7 +318,6 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_store_4d(&tmDQ, sDO, 0, t * kTile, h, b);
       tma_store_commit();
     }
-    stamp(10);
     if (g.cls) {
       // rows 0..63 of G: dV_0^T[d][key] in columns 0..31 ; rows 64..127: dK_0^T[d][key] in columns 32..63
       const int which = row < 64 ? 1 : 0;             // gacc[..., 0] = dK, gacc[..., 1] = dV
@@ -350,9 +329,7 @@ attn_bwd_dq_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) atomicAdd(dst + (16 * hc + cc) * DH, __uint_as_float(v[cc]));
     }
-    stamp(11);
     if (threadIdx.x == 0) tma_store_wait_read();
-    stamp(12);
   }
 
   tc_fence_before();
@@ -408,12 +385,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   const TileGeom g = p.g;
   const int nq = g.nband;
   const int npass = (nq + PASS - 1) / PASS;
-  long long* tl = nullptr;
-  if (p.timeline && lane == 0 && (warp == 0 || warp == 3 || warp == 4))
-    tl = p.timeline + ((((int64_t)gridDim.z * gridDim.y * gridDim.x) + (((int64_t)b * gridDim.y + h) * gridDim.x + t)) * 3 +
-                       (warp == 0 ? 0 : warp == 3 ? 1 : 2)) * 16;
-  auto stamp = [&](int k) { if (tl) tl[k] = clock64(); };
-  stamp(0);
   const int c0 = 4 * t;
   const int q_lo = c0 - g.nsup;                       // query block of slot 0
   auto slot_valid = [&](int i) { int qb = q_lo + i; return qb >= 0 && qb < g.nb; };
@@ -442,7 +413,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  stamp(1);
 
   if (warp == 4) {
     {   // warp-convergent issue path
@@ -459,17 +429,14 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
                  make_smem_desc(do_addr + c * PASS * S::SLOT_BYTES + ks * 32, 16, 8 * ROWB, ROWB), idesc_s, ks > 0 ? 1u : 0u);
         }
       };
-      stamp(2);
       mbar_wait(bar_ld, 0);
       tc_fence_after();
-      stamp(3);
       issue_s_dp(0);
       tc_commit_w(bar_sdp + 0);
       uint32_t acc = 0;
       for (int c = 0; c < npass; ++c) {
         mbar_wait(bar_pds + c, 0);
         tc_fence_after();
-        if (c < 4) stamp(4 + 2 * c);
         for (int i = 0; i < PASS && c * PASS + i < nq; ++i) {
           const int slot = c * PASS + i;
 #pragma unroll
@@ -488,7 +455,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         } else {
           tc_commit_w(bar_out);
         }
-        if (c < 4) stamp(5 + 2 * c);
       }
     }
     __syncwarp();
@@ -512,7 +478,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       sNegDelta[i] = dl;
     }
     named_bar_sync(1, 128);
-    stamp(2);
 
     const bool key_global = g.cls && c == 0;           // handled by the dQ pass
     auto slot_live = [&](int i) {
@@ -525,7 +490,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     for (int cpass = 0; cpass < npass; ++cpass) {
       mbar_wait(bar_sdp + cpass, 0);
       tc_fence_after();
-      if (cpass < 4) stamp(3 + 2 * cpass);
       for (int i = 0; i < PASS && cpass * PASS + i < nq; ++i) {
         const int slot = cpass * PASS + i;
         uint32_t pk[16], dsk[16];
@@ -562,12 +526,10 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_pds + cpass);
-      if (cpass < 4) stamp(4 + 2 * cpass);
     }
 
     mbar_wait(bar_out, 0);
     tc_fence_after();
-    stamp(11);
     const float* gk = p.gacc + (((int64_t)b * p.H + h) * 2 + 0) * (kBlock * DH) + lane * DH;
     const float* gv = gk + kBlock * DH;
 #pragma unroll
@@ -602,7 +564,6 @@ attn_bwd_dkv_sm100_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tma_store_commit();
       tma_store_wait_read();
     }
-    stamp(12);
   }
 
   tc_fence_before();
@@ -639,7 +600,6 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
 
   BwdParams p;
   p.kpm = kpm; p.lse = lse; p.delta = delta; p.gacc = gacc;
-  p.timeline = g_bwd_timeline;
   p.L = L; p.H = H; p.g = g;
   p.scale = d->scale; p.scale_log2 = d->scale * kLog2e;
 
@@ -667,12 +627,8 @@ static int launch_bwd(const svae_attn_desc* d, const void* q, const void* k, con
   using SKV = DkvSmem<DH, NS - 1>;
   auto kq = attn_bwd_dq_sm100_kernel<T, DH, NS>;
   auto kkv = attn_bwd_dkv_sm100_kernel<T, DH, NS - 1>;
-  static bool configured = false;       // per template instantiation
-  if (!configured) {
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ::DYN_BYTES));
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, SKV::DYN_BYTES));
-    configured = true;
-  }
+  SVAE_CONFIGURE_SMEM(kq, SQ::DYN_BYTES);
+  SVAE_CONFIGURE_SMEM(kkv, SKV::DYN_BYTES);
   dim3 grid((L + kTile - 1) / kTile, H, B);
   {
     ScopedKernelTimer timer("attn_bwd_dq_sm100", st);

@@ -14,8 +14,6 @@
 // rebalanced with setmaxnreg (softmax 184, epilogue 88, producers 40).  While group 0 runs the CUDA-core softmax of
 // tile i, group 1 works on tile i+1, the epilogue group drains tile i-1, the tensor pipe computes the next S and the
 // TMA engine is already fetching tile i+2.  Same arithmetic as attn_fwd_sm100_kernel.
-#include <stdlib.h>
-
 #include "attn_sm100.cuh"
 
 namespace svae {
@@ -383,23 +381,10 @@ static int launch_fwd_persist(const svae_attn_desc* d, const TileGeom& g, const 
   p.kpm = kpm; p.lse = lse; p.s_dump = nullptr; p.timeline = timeline;
   p.L = d->seq_len; p.H = d->heads; p.g = g;
   p.scale_log2 = d->scale * kLog2e;
-  {
-    const char* e = getenv("SVAE_FWD_STAGGER");
-    p.stagger_cycles = e ? atoi(e) : -1;       // < 0: no ping-pong between the softmax groups (measured faster)
-  }
+  p.stagger_cycles = -1;                       // < 0: no ping-pong between the softmax groups (measured faster)
   auto kern = attn_fwd_persist_sm100_kernel<T, DH>;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0, n = 0;
-    SVAE_CUDA_CHECK(cudaGetDevice(&dev));
-    SVAE_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    sm_count = n;
-  }
-  static bool configured = false;      // per template instantiation
-  if (!configured) {
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
-    configured = true;
-  }
+  const int sm_count = sm_count_of_current_device();
+  SVAE_CONFIGURE_SMEM(kern, S::DYN_BYTES);
   const int tiles_per_seq = (d->seq_len + kTile - 1) / kTile;
   const int num_tiles = tiles_per_seq * d->heads * d->batch;
   const int grid = num_tiles < sm_count ? num_tiles : sm_count;

@@ -334,11 +334,7 @@ static int launch_fwd(const svae_attn_desc* d, const TileGeom& g, const void* q,
   p.scale_log2 = d->scale * kLog2e;
   p.stagger_cycles = 0;
   auto kern = attn_fwd_sm100_kernel<T, DH, NSMAX>;
-  static bool configured = false;   // benign race: attribute set is idempotent
-  if (!configured) {
-    SVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
-    configured = true;
-  }
+  SVAE_CONFIGURE_SMEM(kern, S::DYN_BYTES);
   dim3 grid((d->seq_len + kTile - 1) / kTile, d->heads, d->batch);
   ScopedKernelTimer timer("attn_fwd_sm100", st);
   kern<<<grid, kThreads, S::DYN_BYTES, st>>>(tmQ, tmK, tmV, tmKb, tmVb, tmKb2, tmVb2, tmO, p);

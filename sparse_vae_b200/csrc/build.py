@@ -1,6 +1,9 @@
 """Builds libsvae_b200.so (the C-ABI library of include/sparse_vae_b200.h) in-tree with nvcc for sm_100a.
 
-    python sparse_vae_b200/csrc/build.py [--force] [--verbose]
+    python sparse_vae_b200/csrc/build.py [--force] [--verbose] [--debug]
+
+`--debug` additionally builds libsvae_b200_dbg.so (include/sparse_vae_b200_debug.h): micro-benchmarks of sm_100a
+primitives used by tests/mma_bench.py / tests/pipe_bench.py; nothing of it is linked into the product library.
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
 """
@@ -17,10 +20,13 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
 BUILD = HERE / 'build'
 LIB = HERE / 'libsvae_b200.so'
-SOURCES = ['abi.cu', 'bottleneck.cu', 'attn_exact.cu', 'attn_fwd_sm100.cu', 'attn_fwd_persist_sm100.cu', 'attn_bwd_sm100.cu', 'attn_dispatch.cu',
-           'debug_mma_bench.cu', 'debug_pipe_bench.cu', 'optim.cu', 'layernorm.cu', 'vocab_ce.cu', 'rotary.cu', 'colsum.cu',
+DEBUG_LIB = HERE / 'libsvae_b200_dbg.so'
+SOURCES = ['abi.cu', 'bottleneck.cu', 'attn_exact.cu', 'attn_fwd_sm100.cu', 'attn_fwd_persist_sm100.cu', 'attn_bwd_sm100.cu',
+           'attn_bwd1_sm100.cu', 'attn_dispatch.cu', 'optim.cu', 'layernorm.cu', 'vocab_ce.cu', 'rotary.cu', 'colsum.cu',
            'decode_attn.cu', 'sampling.cu', 'residual.cu']
-HEADERS = ['common.cuh', 'sm100_ptx.cuh', 'attn_sm100.cuh', '../../include/sparse_vae_b200.h']
+DEBUG_SOURCES = ['debug_mma_bench.cu', 'debug_pipe_bench.cu', 'abi.cu']
+HEADERS = ['common.cuh', 'sm100_ptx.cuh', 'attn_sm100.cuh', '../../include/sparse_vae_b200.h',
+           '../../include/sparse_vae_b200_debug.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 
@@ -32,24 +38,26 @@ def _nvcc() -> str:
     raise RuntimeError('nvcc not found')
 
 
-def _stamp() -> str:
+def _stamp(sources) -> str:
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS + ['build.py']:
+    for f in sources + HEADERS + ['build.py']:
         h.update((HERE / f).read_bytes())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> Path:
+    """Builds the product library; with debug=True the micro-benchmark library instead."""
     BUILD.mkdir(exist_ok=True)
-    stamp_file = HERE / 'libsvae_b200.stamp'      # travels with the .so (build/ does not)
-    stamp = _stamp()
+    SOURCES, LIB = (DEBUG_SOURCES, DEBUG_LIB) if debug else (globals()['SOURCES'], globals()['LIB'])
+    stamp_file = LIB.with_suffix('.stamp')        # travels with the .so (build/ does not)
+    stamp = _stamp(SOURCES)
     if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB
     nvcc = _nvcc()
     extra = ['-Xptxas', '-v'] if verbose else []
 
     def compile_one(src: str):
-        obj = BUILD / (src.replace('.cu', '.o'))
+        obj = BUILD / (src.replace('.cu', '.dbg.o' if debug else '.o'))
         cmd = [nvcc, *NVCC_FLAGS, *extra, '-c', str(HERE / src), '-o', str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
@@ -73,3 +81,5 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    if '--debug' in sys.argv:
+        print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, debug=True))

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/sparse_vae_b200.h"
 
 namespace svae {
@@ -29,6 +31,23 @@ int cuda_fail(cudaError_t e, const char* what);
       return (code);                                                  \
     }                                                                 \
   } while (0)
+
+// ---- opt-in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute, set once per device and kernel.
+// Expands to a block with its own static mask, so every call site (= kernel instantiation) keeps its own record.
+#define SVAE_CONFIGURE_SMEM(kernel, bytes)                                                            \
+  do {                                                                                                \
+    static std::atomic<unsigned long long> _done[2] = {{0ull}, {0ull}};                              \
+    int _dev = 0;                                                                                     \
+    SVAE_CUDA_CHECK(cudaGetDevice(&_dev));                                                            \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                              \
+    if (!(_done[(_dev >> 6) & 1].load(std::memory_order_acquire) & _bit)) {                           \
+      SVAE_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      _done[(_dev >> 6) & 1].fetch_or(_bit, std::memory_order_release);                               \
+    }                                                                                                 \
+  } while (0)
+
+// number of SMs of the current device (cached per device)
+int sm_count_of_current_device();
 
 // ---- optional per-kernel device timing (svae_profile_begin / svae_profile_end) ---------------------
 // When enabled, every kernel launch of the library is bracketed by two CUDA events on its own stream.

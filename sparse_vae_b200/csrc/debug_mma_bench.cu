@@ -2,6 +2,7 @@
 // (M = 128, K = 16, variable N; A from SMEM or TMEM; one or two issuing warps).  Not part of the product path;
 // it exists to size the MMA instruction counts of the attention kernels (profiles/README.md).
 #include "attn_sm100.cuh"
+#include "../../include/sparse_vae_b200_debug.h"
 
 namespace svae {
 namespace sm100 {
@@ -41,8 +42,34 @@ __global__ void __launch_bounds__(96, 1) mma_issue_bench_kernel(int variant, int
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const bool ts = variant & 1, mn = variant & 2, two = variant & 4, conv = variant & 8;
-  if (conv && warp < (two ? 2 : 1)) {
+  const bool ts = variant & 1, mn = variant & 2, two = variant & 4, conv = variant & 8, unrolled = variant & 16;
+  if (unrolled && warp < (two ? 2 : 1)) {
+    // fully unrolled groups of 16 MMAs whose descriptors differ by compile-time offsets (how a kernel with a fixed
+    // schedule issues them), warp-convergent
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 32 * 1024);
+    const uint32_t idesc = make_idesc(128, n, 1, 0, mn ? 1 : 0);
+    const uint32_t d = tmem_base + warp * 256;
+    const uint32_t ta = tmem_base + 128 + warp * 256;
+    const long long t0 = clock64();
+    for (int g = 0; g < count / 16; ++g) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint64_t bd = mn ? make_smem_desc(b_addr + (i & 7) * 2048, 4096, 1024, 128)
+                               : make_smem_desc(b_addr + (i & 3) * 32, 16, 1024, 128);
+        if (ts) mma_ts_e(d, ta + (i & 7) * 8, bd, idesc, (g | i) > 0);
+        else mma_ss_e(d, make_smem_desc(a_addr + (i & 3) * 32, 16, 1024, 128), bd, idesc, (g | i) > 0);
+      }
+    }
+    const long long t1 = clock64();
+    if (elect_one()) tc_commit(&bars[warp]);
+    __syncwarp();
+    mbar_wait(&bars[warp], 0);
+    const long long t2 = clock64();
+    if (lane == 0) {
+      out[warp * 2 + 0] = t1 - t0;
+      out[warp * 2 + 1] = t2 - t0;
+    }
+  } else if (conv && warp < (two ? 2 : 1)) {
     const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + 32 * 1024);
     const uint32_t idesc = make_idesc(128, n, 1, 0, mn ? 1 : 0);
     const uint32_t d = tmem_base + warp * 256;

@@ -4,6 +4,7 @@
 // w % 4).  out[w] = clock64 cycles of warp w for `iters` iterations of an 8-instruction unrolled body.
 // Not part of the product path: it sizes the kernels (profiles/README.md).
 #include "attn_sm100.cuh"
+#include "../../include/sparse_vae_b200_debug.h"
 
 namespace svae {
 namespace sm100 {

@@ -40,6 +40,11 @@ class _Bucket:
         every `.grad` at its slice: one multi-tensor launch on CUDA (csrc/optim.cu), plain copies elsewhere."""
         todo = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         stale = [v for v, p in zip(self.views, self.params) if p.grad is None]
+        # a gradient that already lives in its bucket slice (the step started with gradients kept, e.g.
+        # zero_grad(set_to_none=False): autograd accumulated straight into the view) still needs the 1/world factor
+        aliased = [v for v, p in zip(self.views, self.params) if p.grad is not None and p.grad.data_ptr() == v.data_ptr()]
+        if aliased and scale != 1.0:
+            torch._foreach_mul_(aliased, scale)
         if todo:
             dst, src = [v for v, _ in todo], [g for _, g in todo]
             fused = self.flat.is_cuda and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in src) \
@@ -131,8 +136,10 @@ class GradientAllReducer:
             for b in self.buckets:
                 self._launch(b)
         for b in self.buckets:
-            if b.pending > 0 and b.pending < len(b.params) and b.work is None:
-                self._launch(b)               # some parameter of the bucket got no gradient this step
+            if b.work is None and self.sync:
+                # some (or all) parameters of the bucket got no gradient on THIS rank this step: their slices are
+                # zero-filled and the bucket is reduced anyway, so that every rank issues the same collectives
+                self._launch(b)
             if b.work is not None:
                 b.work.wait()
                 b.work = None

@@ -7,6 +7,8 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from sparse_vae_b200 import _native as N  # noqa: E402
 
+DBG = N.load_debug()      # libsvae_b200_dbg.so: `python sparse_vae_b200/csrc/build.py --debug`
+
 out = torch.zeros(64, dtype=torch.int64, device='cuda')
 iters = 256
 names = ['MUFU.EX2', 'F2FP bf16x2 pack', 'FFMA', 'FMNMX3', 'tcgen05.ld x32 (4 KB)', 'tcgen05.st x16 (2 KB)', 'softmax step (4 elem)', 'softmax step, 96 elem unrolled', 'fwd softmax pass 2 (160 scores in regs)', 'fwd softmax pass 1 + 2 (5 LDTM + max + exp)']
@@ -16,7 +18,7 @@ for mode, name in enumerate(names):
     for warps in (1, 4, 8):
         for _ in range(2):
             out.zero_()
-            N.check(N.lib.svae_debug_pipe_bench(mode, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
+            N.check(DBG.svae_debug_pipe_bench(mode, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
             torch.cuda.synchronize()
         cyc = out[:warps].max().item() / (iters * {6: 4, 7: 48, 8: 1, 9: 1}.get(mode, 8))
         row.append(f'{warps:2d} warps {cyc:7.2f}')
@@ -29,7 +31,7 @@ for mode, name in ((4, 'tcgen05.ld x32 (4 KB)'), (5, 'tcgen05.st x16 (2 KB)'), (
     for warps in (5,):
         for _ in range(2):
             out.zero_()
-            N.check(N.lib.svae_debug_pipe_bench(mode | 0x100, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
+            N.check(DBG.svae_debug_pipe_bench(mode | 0x100, warps, iters, out.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bench')
             torch.cuda.synchronize()
         cyc = out[:warps - 1].max().item() / (iters * {6: 4, 7: 48, 8: 1, 9: 1}.get(mode, 8))
         row.append(f'{warps - 1} warps + MMA {cyc:8.2f}  (MMA groups issued meanwhile: {out[62].item()})')

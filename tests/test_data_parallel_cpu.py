@@ -45,11 +45,14 @@ def _worker(rank, world, port, out):
     opt_ref = torch.optim.SGD(ref.parameters(), lr=0.1)
     g = torch.Generator().manual_seed(1)
     ok = True
-    for step in range(4):
+    for step in range(6):
         x = torch.randn(world * 6, 8, generator=g)
         y = torch.randn(world * 6, 4, generator=g)
         xs, ys = x[rank * 6:(rank + 1) * 6], y[rank * 6:(rank + 1) * 6]
-        reducer.zero_grad()
+        if step >= 4:       # gradients kept and zeroed in place: autograd accumulates straight into the bucket views
+            model.zero_grad(set_to_none=False)
+        else:
+            reducer.zero_grad()
         if step % 2:                              # gradient accumulation over two micro-batches: reduce after the last one
             half = xs.shape[0] // 2
             reducer.sync = False

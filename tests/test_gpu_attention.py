@@ -14,11 +14,14 @@ import torch
 sys.path.insert(0, str(Path(__file__).parent))
 sys.path.insert(0, str(Path(__file__).parent / 'golden'))
 import make_golden as mg  # noqa: E402
-from util import make_padding, make_qkv, oracle_attention, rel_err  # noqa: E402
+from util import block_rel_err, make_padding, make_qkv, oracle_attention, rel_err  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2, torch.float16: 1e-2}
+# per-32-row-block bound (util.block_rel_err): each block against its OWN scale, so that a wrong low-magnitude region
+# (a mis-masked padded block, a tile edge) cannot hide behind the tensor maximum
+BLOCK_TOL = {torch.float32: 1e-3, torch.bfloat16: 5e-2, torch.float16: 5e-2}
 
 
 def _sv():
@@ -43,10 +46,16 @@ def run_case(B, H, L, Dh, dtype, window=4, causal=True, cls=True, lengths=None, 
         out.backward(dout)
         ref_out, rdq, rdk, rdv = oracle_attention(q, k, v, cfg, pad, dout)
         errs = dict(out=rel_err(out, ref_out), dq=rel_err(q.grad, rdq), dk=rel_err(k.grad, rdk), dv=rel_err(v.grad, rdv))
+        blk = dict(out=block_rel_err(out, ref_out), dq=block_rel_err(q.grad, rdq), dk=block_rel_err(k.grad, rdk),
+                   dv=block_rel_err(v.grad, rdv))
     else:
-        errs = dict(out=rel_err(out, oracle_attention(q, k, v, cfg, pad)))
+        ref_out = oracle_attention(q, k, v, cfg, pad)
+        errs = dict(out=rel_err(out, ref_out))
+        blk = dict(out=block_rel_err(out, ref_out))
     bad = {n: e for n, e in errs.items() if not e <= tol}
     assert not bad, f"rel err over {tol}: {bad} (all: {errs})"
+    bad = {n: e for n, e in blk.items() if not e <= BLOCK_TOL[dtype]}
+    assert not bad, f"per-block rel err over {BLOCK_TOL[dtype]}: {bad} (all: {blk})"
     return errs
 
 

@@ -1,0 +1,107 @@
+"""GPU, world_size 2, NCCL: two ranks with half the batch each must reproduce the loss and
+gradients of one process with the whole batch -- both loss terms are batch means (core/continuous_autoencoder.py:47,
+core/language_model.py:161-170), so the averaged per-rank gradient IS the global-batch gradient.  Needs two GPUs on
+the box (skipped otherwise; run it with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+B_GLOBAL, L = 4, 512
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _model(dev):
+    import sparse_vae_b200 as sv
+    from sparse_vae_b200.core.lightning_shim import to_attrdict
+    torch.manual_seed(7295)
+    hp = sv.TransformerVAEHparams(d_model=512, num_layers=4, num_heads=8, latent_depth=32)
+    model = sv.TransformerVAE(to_attrdict(hp)).to(dev)
+    model.initialize_weights()
+    model.train()
+    model.validate_posterior = False
+    for m in model.modules():                      # dropout draws differ between the two decompositions of the batch
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, 'dropout_p'):
+            m.dropout_p = 0.0
+    # the reparameterisation noise is drawn per flat element index of the rank's own [rows, latent] tensor, so two
+    # ranks with half the rows each see different eps than one process with all rows: take it out of the comparison
+    # with sigma = exp(-15) (the KL term and its gradient stay, they do not depend on eps)
+    with torch.no_grad():
+        model.q_of_z_given_x.linear.bias[hp.latent_depth:] = -30.0
+    return model
+
+
+def _batch(dev, lo, hi):
+    from sparse_vae_b200.synthetic import synthetic_tokens, to_device
+    host = synthetic_tokens(B_GLOBAL, L, seed=11, lengths=[L, L - 37, L - 200, L - 5])
+    host = {k: v[lo:hi] for k, v in host.items()}
+    return to_device(host, dev, non_blocking=False)
+
+
+def _step(model, batch, reducer=None):
+    model.zero_grad(set_to_none=True)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        out = model.training_step(batch, 0)
+    out['loss'].backward()
+    if reducer is not None:
+        reducer.finish()
+    return out['loss'].detach().float()
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from sparse_vae_b200.data_parallel import GradientAllReducer, init_distributed
+    r, local, w = init_distributed('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    model = _model(dev)
+    reducer = GradientAllReducer(model, bucket_mb=4.0)
+    per = B_GLOBAL // world
+    res = {}
+    for it in range(2):                            # step 0 builds the buckets, step 1 runs the overlapped path
+        loss = _step(model, _batch(dev, rank * per, (rank + 1) * per), reducer)
+        lsum = loss.clone()
+        dist.all_reduce(lsum)
+        flat = torch.cat([p.grad.flatten().float() for p in model.parameters() if p.grad is not None])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        res[it] = dict(loss=(lsum / world).item(), gnorm=flat.norm().item(), same=all(torch.equal(gathered[0], t) for t in gathered),
+                       grad=flat.cpu() if rank == 0 else None)
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_rank_nccl_step_matches_single_process():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        multi = dict(out)
+    dev = torch.device('cuda', 0)
+    model = _model(dev)
+    for it in range(2):
+        loss = _step(model, _batch(dev, 0, B_GLOBAL)).item()
+        flat = torch.cat([p.grad.flatten().float() for p in model.parameters() if p.grad is not None]).cpu()
+        m = multi[0][it]
+        assert multi[0][it]['same'] and multi[1][it]['same'], 'ranks disagree bitwise after the all-reduce'
+        assert abs(m['loss'] - loss) <= 1e-5 * abs(loss), (m['loss'], loss)
+        assert abs(m['gnorm'] - flat.norm().item()) <= 1e-3 * flat.norm().item(), (m['gnorm'], flat.norm().item())
+        # element-wise: bf16 GEMMs with different batch decompositions round differently; the bound is relative to the
+        # gradient's scale
+        err = (m['grad'] - flat).abs().max().item() / flat.abs().max().item()
+        assert err <= 2e-2, err

@@ -18,6 +18,24 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).abs().max().item()) / (denom if denom > 0 else 1.0)
 
 
+def block_rel_err(a: torch.Tensor, b: torch.Tensor, block: int = 32, floor: float = 1e-3) -> float:
+    """Worst per-block error of a [B, H, L, Dh] tensor: max|a-b| over each (batch, head, 32-row block) relative to
+    max|b| over THAT block (not the whole tensor), so that a wrong low-magnitude region -- a mis-masked padded block,
+    a tile edge -- cannot hide behind the tensor's largest entries.  Blocks whose reference is (nearly) zero are held
+    to `floor` times the tensor's scale instead."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if not torch.equal(torch.isnan(a), torch.isnan(b)):
+        return float('inf')
+    nan = torch.isnan(b)
+    a, b = a.masked_fill(nan, 0.0), b.masked_fill(nan, 0.0)
+    B, H, L, D = b.shape
+    nb = L // block
+    d = (a - b).abs()[:, :, :nb * block].reshape(B, H, nb, block * D).amax(-1)
+    scale = b.abs()[:, :, :nb * block].reshape(B, H, nb, block * D).amax(-1)
+    gmax = b.abs().max().item()
+    return (d / scale.clamp_min(floor * (gmax if gmax > 0 else 1.0))).max().item()
+
+
 def make_qkv(B, H, L, Dh, dtype, device, seed=0, strided=True, requires_grad=False):
     """q, k, v as the reference hands them to the op: [B,H,L,Dh] views of [B,L,H*Dh] (core/attention.py:76)."""
     g = torch.Generator(device='cpu').manual_seed(seed)
