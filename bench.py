@@ -611,20 +611,6 @@ def main_generation(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), n
 
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))     # one step = 4095 graph replays (~1.7 s)
-    for i in range(warmup):
-        sample(i)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms, n = timed(sample, steps)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, n_e2e = timed(lambda i: sample(i, True), steps)
-    N.profile_begin()
-    sample(0)
-    torch.cuda.synchronize()
-    prof = N.profile_end()
-
     # teacher-forced reconstruct of the same volume, in chunks of 32 samples (full logits would be 69 GB)
     chunks = [to_device(synthetic_tokens(32, L, seed=c), dev)['token_ids'] for c in range(B // 32)]
 
@@ -642,6 +628,20 @@ def main_generation(args):
         rec_ms, _ = timed(reconstruct_all, 2)
         rec = {'what': f'teacher-forced decoder forward + argmax, {B} x {L} tokens in chunks of 32, bf16', 'ms': rec_ms / 2,
                'tokens_per_s': world * B * L / (rec_ms / 2 * 1e-3)}
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))     # one step = 4095 graph replays (~1.7 s)
+    for i in range(warmup):
+        sample(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, n = timed(sample, steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, n_e2e = timed(lambda i: sample(i, True), steps)
+    N.profile_begin()
+    sample(0)
+    torch.cuda.synchronize()
+    prof = N.profile_end()
+
     if rank == 0:
         per_kernel = {k: {'launches': v['launches'], 'us_per_launch': v['ms'] / v['launches'] * 1e3} for k, v in prof.items()
                       if v['launches']}

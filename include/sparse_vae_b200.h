@@ -53,6 +53,7 @@ extern "C" {
 
 /* svae_attn_desc.flags */
 #define SVAE_ATTN_FORCE_EXACT  1   /* run 16-bit inputs through the exact CUDA-core path (cross-check / debugging) */
+#define SVAE_ATTN_BWD_TWO_PASS 4   /* backward: use the two-pass kernels even where the one-pass kernel applies (cross-check) */
 #define SVAE_ATTN_PERSISTENT   2   /* forward: persistent warp-specialised kernel (what the host wrapper selects for <= 8 key slots;
                                       without the flag: one CTA per tile, also used for wider windows and score dumps) */
 
@@ -104,8 +105,9 @@ SVAE_API int svae_attn_fwd(const svae_attn_desc* desc, const void* q, const void
 /* Which kernels svae_attn_bwd will run for this problem: the tcgen05 kernels need 16-bit tensors, head_dim 64 and
  * a band of <= 13 key blocks; everything else takes the exact CUDA-core kernels (20-40x slower; the host wrapper
  * warns when 16-bit tensors end up there).  < 0: invalid descriptor. */
-#define SVAE_BWD_PATH_TCGEN05 0
+#define SVAE_BWD_PATH_TCGEN05 0            /* one pass over the sequence (causal, window <= 4: the reference's default) */
 #define SVAE_BWD_PATH_EXACT   1
+#define SVAE_BWD_PATH_TCGEN05_TWO_PASS 2   /* dQ pass + dK/dV pass (non-causal layouts, windows 5..10) */
 SVAE_API int svae_attn_bwd_path(const svae_attn_desc* desc);
 
 SVAE_API size_t svae_attn_bwd_workspace_bytes(const svae_attn_desc* desc);

@@ -17,6 +17,7 @@ LIB_PATH = _HERE / 'csrc' / 'libsvae_b200.so'
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ATTN_FORCE_EXACT = 1
 ATTN_PERSISTENT = 2
+ATTN_BWD_TWO_PASS = 4
 ATTN_PERSISTENT_DEFAULT = True       # persistent warp-specialised forward (95 us vs 105 us at the C2 shape)
 BOTTLENECK_WORKSPACE_BYTES = 8448
 ABI_VERSION = 1

@@ -160,6 +160,8 @@ class SparseAttention:
         flags = N.ATTN_FORCE_EXACT if force_exact else 0
         if _env_flag('SVAE_ATTN_PERSISTENT', N.ATTN_PERSISTENT_DEFAULT):
             flags |= N.ATTN_PERSISTENT
+        if _env_flag('SVAE_ATTN_BWD_TWO_PASS', False):      # cross-check of the one-pass backward (tests)
+            flags |= N.ATTN_BWD_TWO_PASS
         out = _SparseAttentionFn.apply(q, k, v, kpm, self, flags)
         for _ in range(4 - original_dims):
             out = out.squeeze(0)

@@ -19,6 +19,10 @@ bool fwd_persist_supported(const svae_attn_desc*);
 int fwd_persist(const svae_attn_desc*, const void*, const void*, const void*, const float*, void*, float*, long long*, cudaStream_t);
 size_t bwd_workspace(const svae_attn_desc*);
 bool bwd_supported(const svae_attn_desc*);
+bool bwd1_supported(const svae_attn_desc*);
+size_t bwd1_workspace(const svae_attn_desc*);
+int bwd1(const svae_attn_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
+         const float*, void*, void*, void*, void*, cudaStream_t);
 int bwd(const svae_attn_desc*, const void*, const void*, const void*, const void*, const void*, const float*,
         const float*, void*, void*, void*, void*, cudaStream_t);
 
@@ -61,6 +65,13 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int 
     if (keys[i] == key) { *map = maps[i]; return SVAE_OK; }
   EncodeTiledFn fn = get_encode_fn();
   SVAE_REQUIRE(fn != nullptr, SVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  // cuTensorMapEncodeTiled is a DRIVER call: on a thread that has not made a runtime call yet (PyTorch's autograd
+  // thread entering the backward) no context is current and it fails with CUDA_ERROR_INVALID_CONTEXT
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    SVAE_CUDA_CHECK(cudaFree(nullptr));
+    context_bound = true;
+  }
   const int64_t es = 2;
   cuuint64_t dims[4] = {(cuuint64_t)Dh, (cuuint64_t)L, (cuuint64_t)H, (cuuint64_t)B};
   // a size-1 dimension may carry any stride; give it a harmless, valid one
@@ -112,6 +123,12 @@ static bool use_exact(const svae_attn_desc* d) {
   return d->dtype == SVAE_DTYPE_F32 || (d->flags & SVAE_ATTN_FORCE_EXACT);
 }
 
+// one pass over the sequence (attn_bwd1_sm100.cu) unless the geometry is outside it or the caller asks for the
+// two-pass kernels (attn_bwd_sm100.cu: non-causal layouts and windows 5..10)
+static bool use_one_pass(const svae_attn_desc* d) {
+  return !(d->flags & SVAE_ATTN_BWD_TWO_PASS) && sm100::bwd1_supported(d);
+}
+
 }  // namespace svae
 
 using namespace svae;
@@ -155,13 +172,14 @@ extern "C" int svae_attn_fwd_debug(const svae_attn_desc* d, const void* q, const
 extern "C" size_t svae_attn_bwd_workspace_bytes(const svae_attn_desc* d) {
   if (validate(d, true)) return 0;
   if (use_exact(d) || !sm100::bwd_supported(d)) return exact_bwd_workspace(d);
+  if (use_one_pass(d)) return sm100::bwd1_workspace(d);
   return sm100::bwd_workspace(d);
 }
 
 extern "C" int svae_attn_bwd_path(const svae_attn_desc* d) {
   if (validate(d, true)) return -1;
   if (use_exact(d) || !sm100::bwd_supported(d)) return SVAE_BWD_PATH_EXACT;
-  return SVAE_BWD_PATH_TCGEN05;
+  return use_one_pass(d) ? SVAE_BWD_PATH_TCGEN05 : SVAE_BWD_PATH_TCGEN05_TWO_PASS;
 }
 
 extern "C" int svae_attn_bwd(const svae_attn_desc* d, const void* q, const void* k, const void* v, const void* out,
@@ -182,6 +200,7 @@ extern "C" int svae_attn_bwd(const svae_attn_desc* d, const void* q, const void*
                   tma_ok(dout, d->do_stride, d->heads, d->batch, d->seq_len) && tma_ok(dq, d->dq_stride, d->heads, d->batch, d->seq_len) &&
                   tma_ok(dk, d->dk_stride, d->heads, d->batch, d->seq_len) && tma_ok(dv, d->dv_stride, d->heads, d->batch, d->seq_len);
   SVAE_REQUIRE(ok, SVAE_ERR_INVALID, "svae_attn_bwd: 16-bit tensors must be 16-byte aligned with strides that are multiples of 8 elements");
+  if (use_one_pass(d)) return sm100::bwd1(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
   return sm100::bwd(d, q, k, v, out, dout, lse, kpm, dq, dk, dv, workspace, st);
 }
 
