@@ -21,6 +21,12 @@ SVAE_API int svae_debug_mma_bench(int variant, int n, int count, long long* out,
  * 6 the softmax step (FFMA, EX2, FADD, pack).  out: int64[64]. */
 SVAE_API int svae_debug_pipe_bench(int mode, int warps, int iters, long long* out, void* stream);
 
+/* libsvae_b200_dbg.so also holds the product kernels compiled with -DSVAE_DEBUG_BUILD (same entry points as
+ * sparse_vae_b200.h).  When non-NULL, the next one-pass svae_attn_bwd launches write, per CTA and warp, the cycles spent
+ * in every kind of wait: int64 [num_ctas][16 warps][12] = {full, stat, s_ready, p_ready, u_free, group, ds_free,
+ * acc_ready, acc_free, free, total cycles of the CTA, tiles of the CTA}.  Process-global; debug library only. */
+SVAE_API void svae_debug_set_b1_timeline(long long* timeline);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,10 @@ from pathlib import Path
 import torch
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / 'csrc' / 'libsvae_b200.so'
+import os as _os
+
+# SVAE_LIB_VARIANT=<suffix>: an experimental build of the same library (csrc/build.py --variant), kernel experiments only
+LIB_PATH = _HERE / 'csrc' / f"libsvae_b200{_os.environ.get('SVAE_LIB_VARIANT', '')}.so"
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ATTN_FORCE_EXACT = 1

@@ -24,7 +24,7 @@ DEBUG_LIB = HERE / 'libsvae_b200_dbg.so'
 SOURCES = ['abi.cu', 'bottleneck.cu', 'attn_exact.cu', 'attn_fwd_sm100.cu', 'attn_fwd_persist_sm100.cu', 'attn_bwd_sm100.cu',
            'attn_bwd1_sm100.cu', 'attn_dispatch.cu', 'optim.cu', 'layernorm.cu', 'vocab_ce.cu', 'rotary.cu', 'colsum.cu',
            'decode_attn.cu', 'sampling.cu', 'residual.cu']
-DEBUG_SOURCES = ['debug_mma_bench.cu', 'debug_pipe_bench.cu', 'abi.cu']
+DEBUG_SOURCES = ['debug_mma_bench.cu', 'debug_pipe_bench.cu'] + SOURCES       # product sources again, with -DSVAE_DEBUG_BUILD
 HEADERS = ['common.cuh', 'sm100_ptx.cuh', 'attn_sm100.cuh', '../../include/sparse_vae_b200.h',
            '../../include/sparse_vae_b200_debug.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -45,20 +45,23 @@ def _stamp(sources) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False, debug: bool = False) -> Path:
-    """Builds the product library; with debug=True the micro-benchmark library instead."""
+def build(force: bool = False, verbose: bool = False, debug: bool = False, defines=(), suffix: str = '') -> Path:
+    """Builds the product library; with debug=True the micro-benchmark library instead.  `defines` / `suffix`: an
+    experimental variant of the product library (extra -D flags) under its own name, e.g. libsvae_b200_m1.so."""
     BUILD.mkdir(exist_ok=True)
     SOURCES, LIB = (DEBUG_SOURCES, DEBUG_LIB) if debug else (globals()['SOURCES'], globals()['LIB'])
+    if suffix:
+        LIB = LIB.with_name(LIB.stem + suffix + '.so')
     stamp_file = LIB.with_suffix('.stamp')        # travels with the .so (build/ does not)
-    stamp = _stamp(SOURCES)
+    stamp = _stamp(SOURCES) + ' ' + ' '.join(defines)
     if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB
     nvcc = _nvcc()
     extra = ['-Xptxas', '-v'] if verbose else []
 
     def compile_one(src: str):
-        obj = BUILD / (src.replace('.cu', '.dbg.o' if debug else '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, *extra, '-c', str(HERE / src), '-o', str(obj)]
+        obj = BUILD / (src.replace('.cu', ('.dbg' if debug else '') + suffix + '.o'))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *(['-DSVAE_DEBUG_BUILD'] if debug else []), *[f'-D{d}' for d in defines], '-c', str(HERE / src), '-o', str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
@@ -83,3 +86,6 @@ if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
     if '--debug' in sys.argv:
         print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv, debug=True))
+    if '--variant' in sys.argv:          # --variant <suffix> <DEFINE=VALUE> ...
+        i = sys.argv.index('--variant')
+        print(build(force='--force' in sys.argv, defines=tuple(sys.argv[i + 2:]), suffix=sys.argv[i + 1]))

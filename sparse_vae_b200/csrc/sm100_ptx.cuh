@@ -31,23 +31,58 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// SVAE_MBAR_MODE (experiments, tests/mbar_modes.sh): 0 = mbarrier.try_wait with the system-dependent suspend time,
+// 1 = mbarrier.test_wait (never suspends: pure polling), 2 = try_wait with a suspend-time hint of SVAE_MBAR_HINT_NS
+#ifndef SVAE_MBAR_MODE
+#define SVAE_MBAR_MODE 0
+#endif
+#ifndef SVAE_MBAR_HINT_NS
+#define SVAE_MBAR_HINT_NS 32
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if SVAE_MBAR_MODE == 1
+  asm volatile(
+      "{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#elif SVAE_MBAR_MODE == 2
+  asm volatile(
+      "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SVAE_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.  Kept inline and
 // minimal (no printf): an out-of-line slow path makes ptxas ignore setmaxnreg and spill the softmax registers.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  // try_wait suspends the thread for a hardware-defined interval by itself; the clock (expensive to read, and a
+  // serialising instruction) is only consulted once a wait has lasted far longer than any legitimate one
+#pragma unroll 1
+  for (int i = 0; i < (SVAE_MBAR_MODE == 0 ? 4096 : 1 << 20); ++i)
+    if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 2 GHz
   }
+}
+
+// One arrival per warp (called by all 32 lanes, warp-uniform argument): __syncwarp() extends the release of the
+// arriving lane to the other lanes' earlier writes.  (Measured the other way round for WAITS: one polling lane per
+// warp followed by __syncwarp() is 3.5x SLOWER than all 32 lanes executing try_wait convergently -- the hardware
+// suspends a convergent warp, a single-lane loop spins through divergence barriers.)
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
 // ---- TMA -----------------------------------------------------------------------------------------

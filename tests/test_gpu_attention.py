@@ -257,3 +257,59 @@ def test_full_size_backward_slice():
     assert rel_err(sl(q.grad), rdq) <= 1e-2
     assert rel_err(sl(k.grad), rdk) <= 1e-2
     assert rel_err(sl(v.grad), rdv) <= 1e-2
+
+
+# ---------------------------------------------------------------- one-pass backward (attn_bwd1_sm100.cu)
+def _grads(cfg, q, k, v, dout, kpm=None):
+    q.grad = k.grad = v.grad = None
+    cfg(q, k, v, key_padding_mask=kpm).backward(dout)
+    return q.grad.clone(), k.grad.clone(), v.grad.clone()
+
+
+@pytest.mark.parametrize('B,H,L,window,cls,lengths', [
+    (1, 1, 128, 4, True, None),            # one key tile: no halo, the global block IS the diagonal
+    (1, 2, 160, 4, True, [150]),           # partial last tile (L % 128 != 0) + padding
+    (5, 8, 4096, 4, True, None),           # 1280 tiles on 148 CTAs: segments start mid-sequence (pre-tiles), 2-3 partials per sequence
+    (1, 2, 16384, 4, True, None),          # long sequences: several CTAs per sequence
+    (3, 8, 1024, 4, True, [1024, 517, 40]),
+    (2, 8, 640, 2, True, [640, 333]), (2, 8, 640, 1, True, None), (2, 4, 608, 3, False, [608, 500]), (2, 4, 512, 4, False, None),
+])
+def test_one_pass_backward_matches_oracle_and_two_pass(monkeypatch, B, H, L, window, cls, lengths):
+    sv = _sv()
+    dev = torch.device('cuda')
+    cfg = sv.SparseAttention(window_size=window, include_cls=cls, num_heads=H)
+    q, k, v = make_qkv(B, H, L, 64, torch.bfloat16, dev, seed=L + window, requires_grad=True)
+    g = torch.Generator().manual_seed(5)
+    dout = torch.randn(B, L, H * 64, generator=g).to(dev, torch.bfloat16).unflatten(-1, (H, 64)).transpose(1, 2)
+    pad = make_padding(B, L, lengths, dev) if lengths else None
+    kpm = pad * -1e7 if pad is not None else None
+    monkeypatch.setenv('SVAE_ATTN_BWD_TWO_PASS', '0')
+    one = _grads(cfg, q, k, v, dout, kpm)
+    again = _grads(cfg, q, k, v, dout, kpm)
+    monkeypatch.setenv('SVAE_ATTN_BWD_TWO_PASS', '1')
+    two = _grads(cfg, q, k, v, dout, kpm)
+    # bit-deterministic: no atomics anywhere, the global block's partials are summed in segment order
+    for a, b in zip(one, again):
+        assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+    if B * H * L <= 2 * 8 * 4096:          # the fp64 oracle on the CPU is quadratic in L
+        _, rdq, rdk, rdv = oracle_attention(q, k, v, cfg, pad, dout)
+        for nm, got, want in (('dq', one[0], rdq), ('dk', one[1], rdk), ('dv', one[2], rdv)):
+            assert rel_err(got, want) <= 1e-2, nm
+            assert block_rel_err(got, want) <= BLOCK_TOL[torch.bfloat16], nm
+    for nm, a, b in zip(('dq', 'dk', 'dv'), one, two):        # same rounding points, different accumulation order
+        assert rel_err(a, b.float()) <= 4e-3, nm
+
+
+def test_backward_path_selection():
+    import ctypes
+    sv = _sv()
+    from sparse_vae_b200 import _native as N
+    from sparse_vae_b200.core.sparse_attention import _make_desc
+    dev = torch.device('cuda')
+    q, k, v = make_qkv(1, 8, 256, 64, torch.bfloat16, dev)
+    path = lambda cfg, flags=0: N.lib.svae_attn_bwd_path(ctypes.byref(_make_desc(cfg, q, k, v, q, flags)))
+    assert path(sv.SparseAttention()) == 0                                    # one pass
+    assert path(sv.SparseAttention(), N.ATTN_BWD_TWO_PASS) == 2
+    assert path(sv.SparseAttention(window_size=8)) == 2                       # wide windows: two passes
+    assert path(sv.SparseAttention(causal=False)) == 2
+    assert path(sv.SparseAttention(), N.ATTN_FORCE_EXACT) == 1

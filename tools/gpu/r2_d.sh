@@ -1,0 +1,4 @@
+set -x
+cd /root/repo; mkdir -p gpurun_out
+timeout 300 python tests/timeline_bwd1.py > gpurun_out/r2d_timeline_bwd1.log 2>&1; echo "rc=$?" >> gpurun_out/r2d_timeline_bwd1.log
+cat gpurun_out/r2d_timeline_bwd1.log
