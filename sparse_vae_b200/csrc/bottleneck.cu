@@ -109,9 +109,10 @@ __global__ void __launch_bounds__(kBnThreads) bottleneck_fwd_kernel(BnFwdArgs a)
       float4 n4;
       float nv[4];
       if (SHARE) {
-        int64_t li = r0 * D + d;                        // component 0 of call (li / T) / 4
-        int64_t k = li / a.pp.T;
-        n4 = normal4_at(a.pp, li - k * a.pp.T, k >> 2);
+        // r0 = 4*m*R + i  =>  flat index r0*D + d = (4m)*T + (i*D + d) with i*D + d < T: "thread" i*D + d, call m, and the
+        // four rows r0 + j*R are its components j = 0..3 -- no division per element
+        const int64_t m = r0 / (4 * a.rows_per_T), i = r0 - m * 4 * a.rows_per_T;
+        n4 = normal4_at(a.pp, i * D + d, m);
         nv[0] = n4.x; nv[1] = n4.y; nv[2] = n4.z; nv[3] = n4.w;
       }
 #pragma unroll
@@ -205,9 +206,8 @@ __global__ void __launch_bounds__(kBnThreads) bottleneck_bwd_kernel(BnBwdArgs a)
       float4 n4;
       float nv[4];
       if (SHARE) {
-        int64_t li = r0 * D + d;
-        int64_t k = li / a.pp.T;
-        n4 = normal4_at(a.pp, li - k * a.pp.T, k >> 2);
+        const int64_t m = r0 / (4 * a.rows_per_T), i = r0 - m * 4 * a.rows_per_T;
+        n4 = normal4_at(a.pp, i * D + d, m);
         nv[0] = n4.x; nv[1] = n4.y; nv[2] = n4.z; nv[3] = n4.w;
       }
 #pragma unroll
@@ -245,9 +245,177 @@ __global__ void __launch_bounds__(kBnThreads) bottleneck_bwd_kernel(BnBwdArgs a)
   }
 }
 
+// ---- vectorised kernels for the common geometry: T (threads of the emulated ATen launch) a multiple of `latent`, latent
+// even.  Work item q = (m, i): the four rows r0 + j*R (R = T / latent, r0 = 4*m*R + i) share their Philox outputs: element
+// (row r0 + j*R, d) is component j of call m of "thread" i*latent + d -- no division per element.  A lane owns TWO
+// adjacent features: 4-byte loads of the 16-bit inputs (8-byte for fp32), 8-byte stores -> every warp request is a
+// full 128 / 256-byte line.
+#ifndef SVAE_BN_VEC_BLOCKS
+#define SVAE_BN_VEC_BLOCKS 4      // resident blocks per SM the vectorised kernels are compiled for (register cap 64)
+#endif
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+  __device__ static __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  __device__ static __forceinline__ void store(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  __device__ static __forceinline__ float2 load(const __nv_bfloat16* p) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __nv_bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+  }
+};
+template <> struct Pair<__half> {
+  __device__ static __forceinline__ float2 load(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+  __device__ static __forceinline__ void store(__half* p, float a, float b) {
+    *reinterpret_cast<__half2*>(p) = __half2(__float2half_rn(a), __float2half_rn(b));
+  }
+};
+
+__device__ __forceinline__ float comp4(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads, SVAE_BN_VEC_BLOCKS) bottleneck_fwd_vec_kernel(BnFwdArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = kBnThreads / 32;
+  const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
+  const int D = a.latent;
+  const int64_t R = a.rows_per_T;
+  float block_part = 0.f;
+
+  for (int64_t q = (int64_t)blockIdx.x * warps_per_block + warp; q < a.quads; q += (int64_t)gridDim.x * warps_per_block) {
+    const int64_t m = q / R, i = q - m * R;
+    const int64_t r0 = 4 * m * R + i;
+    float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 2 * lane; d < D; d += 64) {
+      const float4 na = normal4_at(a.pp, i * D + d, m), nb = normal4_at(a.pp, i * D + d + 1, m);
+      float2 mu[4], lv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                      // all loads first: eight 128-byte requests in flight per warp
+        const int64_t row = r0 + j * R;
+        if (row < a.rows) {
+          mu[j] = Pair<T>::load(in + row * a.ld + d);
+          lv[j] = Pair<T>::load(in + row * a.ld + D + d);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = r0 + j * R;
+        if (row < a.rows) {
+          const float e0 = round_through<T>(comp4(na, j)), e1 = round_through<T>(comp4(nb, j));
+          const float v0 = expf(lv[j].x), v1 = expf(lv[j].y);
+          const float s0 = sqrtf(v0), s1 = sqrtf(v1);
+          // separate roundings (no FMA) so z and kl match the op-by-op torch evaluation bit for bit
+          const float z0 = __fadd_rn(mu[j].x, __fmul_rn(e0, s0)), z1 = __fadd_rn(mu[j].y, __fmul_rn(e1, s1));
+          const float k0 = __fmul_rn(0.5f, __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(mu[j].x, mu[j].x), v0), lv[j].x), -1.0f));
+          const float k1 = __fmul_rn(0.5f, __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(mu[j].y, mu[j].y), v1), lv[j].y), -1.0f));
+          const int64_t o = row * D + d;
+          Pair<float>::store(a.z + o, z0, z1);
+          Pair<float>::store(a.sigma + o, s0, s1);
+          if (a.kl_elem) Pair<float>::store(a.kl_elem + o, k0, k1);
+          rowsum[j] += k0;                               // (per-lane order d, d + 1: the row sum may differ from the scalar kernel in the last bits)
+          rowsum[j] += k1;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t row = r0 + j * R;
+      if (row < a.rows) {
+        float s = rowsum[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          a.raw_kl[row] = s;
+          block_part += s / (float)a.token_counts[row];
+        }
+      }
+    }
+  }
+
+  // deterministic two-level reduction of kl = mean_b(raw_kl[b] / token_counts[b])
+  __shared__ float warp_part[kBnThreads / 32];
+  __shared__ bool is_last;
+  if (lane == 0) warp_part[warp] = block_part;
+  __syncthreads();
+  unsigned* counter = reinterpret_cast<unsigned*>(a.workspace);
+  float* partials = a.workspace + kBnPartialOffset;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) s += warp_part[w];
+    partials[blockIdx.x] = s;
+    __threadfence();
+    unsigned prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(partials + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      a.kl[0] = s / (float)a.rows;
+      *counter = 0u;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads, SVAE_BN_VEC_BLOCKS) bottleneck_bwd_vec_kernel(BnBwdArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = kBnThreads / 32;
+  const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
+  T* __restrict__ out = reinterpret_cast<T*>(a.dout);
+  const int D = a.latent;
+  const int64_t R = a.rows_per_T;
+  const float dkl = a.dkl ? a.dkl[0] : 0.f;
+
+  for (int64_t q = (int64_t)blockIdx.x * warps_per_block + warp; q < a.quads; q += (int64_t)gridDim.x * warps_per_block) {
+    const int64_t m = q / R, i = q - m * R;
+    const int64_t r0 = 4 * m * R + i;
+    for (int d = 2 * lane; d < D; d += 64) {
+      const float4 na = normal4_at(a.pp, i * D + d, m), nb = normal4_at(a.pp, i * D + d + 1, m);
+      float2 mu[4], lv[4], gz[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = r0 + j * R;
+        if (row < a.rows) {
+          mu[j] = Pair<T>::load(in + row * a.ld + d);
+          lv[j] = Pair<T>::load(in + row * a.ld + D + d);
+          gz[j] = a.dz ? Pair<float>::load(a.dz + row * D + d) : make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = r0 + j * R;
+        if (row < a.rows) {
+          const int64_t o = row * D + d;
+          const float e0 = round_through<T>(comp4(na, j)), e1 = round_through<T>(comp4(nb, j));
+          const float v0 = expf(lv[j].x), v1 = expf(lv[j].y);
+          const float s0 = sqrtf(v0), s1 = sqrtf(v1);
+          float g = dkl / ((float)a.rows * (float)a.token_counts[row]);
+          if (a.draw_kl) g += a.draw_kl[row];
+          float g0 = g, g1 = g, gs0 = 0.f, gs1 = 0.f;
+          if (a.dkl_elem) { const float2 t = Pair<float>::load(a.dkl_elem + o); g0 += t.x; g1 += t.y; }
+          if (a.dsigma) { const float2 t = Pair<float>::load(a.dsigma + o); gs0 = t.x; gs1 = t.y; }
+          const float dmu0 = gz[j].x + g0 * mu[j].x, dmu1 = gz[j].y + g1 * mu[j].y;
+          const float dlv0 = (gz[j].x * e0 + gs0) * 0.5f * s0 + g0 * 0.5f * (v0 - 1.0f);
+          const float dlv1 = (gz[j].y * e1 + gs1) * 0.5f * s1 + g1 * 0.5f * (v1 - 1.0f);
+          Pair<T>::store(out + row * a.ld_out + d, dmu0, dmu1);
+          Pair<T>::store(out + row * a.ld_out + D + d, dlv0, dlv1);
+        }
+      }
+    }
+  }
+}
+
 struct BnPlan {
   PhiloxPlan pp;
   bool share;
+  bool vec;        // the vectorised kernels apply (share, even latent; alignment is checked per call)
   int64_t quads, rows_per_T;
   int grid;
 };
@@ -265,6 +433,11 @@ static int make_plan(int64_t rows, int latent, uint64_t seed, uint64_t offset, i
   p->pp.offset = offset;
   p->pp.T = T;
   p->share = (T % latent == 0);
+#ifdef SVAE_BN_NO_VEC
+  p->vec = false;
+#else
+  p->vec = p->share && latent % 2 == 0;
+#endif
   if (p->share) {
     int64_t R = T / latent;
     p->rows_per_T = R;
@@ -306,9 +479,15 @@ extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dty
               reinterpret_cast<float*>(workspace), p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ScopedKernelTimer timer("bottleneck_fwd", st);
+  // 4 / 8-byte accesses of the vectorised kernel: even leading dimension, aligned bases
+  const size_t es = dtype_size(dtype);
+  const bool vec = p.vec && ld % 2 == 0 && reinterpret_cast<uintptr_t>(mulogvar) % (2 * es) == 0 &&
+                   reinterpret_cast<uintptr_t>(z) % 8 == 0 && reinterpret_cast<uintptr_t>(sigma) % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(kl_elem) % 8 == 0;
 #define SVAE_BN_LAUNCH(T)                                                              \
   do {                                                                                 \
-    if (p.share) bottleneck_fwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a);     \
+    if (vec) bottleneck_fwd_vec_kernel<T><<<p.grid, kBnThreads, 0, st>>>(a);           \
+    else if (p.share) bottleneck_fwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a); \
     else bottleneck_fwd_kernel<T, false><<<p.grid, kBnThreads, 0, st>>>(a);            \
   } while (0)
   switch (dtype) {
@@ -337,9 +516,14 @@ extern "C" int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dty
               p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ScopedKernelTimer timer("bottleneck_bwd", st);
+  const size_t es = dtype_size(dtype);
+  const bool vec = p.vec && ld % 2 == 0 && ld_out % 2 == 0 && reinterpret_cast<uintptr_t>(mulogvar) % (2 * es) == 0 &&
+                   reinterpret_cast<uintptr_t>(d_mulogvar) % (2 * es) == 0 && reinterpret_cast<uintptr_t>(dz) % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(dsigma) % 8 == 0 && reinterpret_cast<uintptr_t>(dkl_elem) % 8 == 0;
 #define SVAE_BN_LAUNCH(T)                                                              \
   do {                                                                                 \
-    if (p.share) bottleneck_bwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a);     \
+    if (vec) bottleneck_bwd_vec_kernel<T><<<p.grid, kBnThreads, 0, st>>>(a);           \
+    else if (p.share) bottleneck_bwd_kernel<T, true><<<p.grid, kBnThreads, 0, st>>>(a); \
     else bottleneck_bwd_kernel<T, false><<<p.grid, kBnThreads, 0, st>>>(a);            \
   } while (0)
   switch (dtype) {

@@ -272,7 +272,8 @@ def _grads(cfg, q, k, v, dout, kpm=None):
     (5, 8, 4096, 4, True, None),           # 1280 tiles on 148 CTAs: segments start mid-sequence (pre-tiles), 2-3 partials per sequence
     (1, 2, 16384, 4, True, None),          # long sequences: several CTAs per sequence
     (3, 8, 1024, 4, True, [1024, 517, 40]),
-    (2, 8, 640, 2, True, [640, 333]), (2, 8, 640, 1, True, None), (2, 4, 608, 3, False, [608, 500]), (2, 4, 512, 4, False, None),
+    # (without the global block a query whose whole window is padding has no finite key: the padded tail stays below window * 32)
+    (2, 8, 640, 2, True, [640, 333]), (2, 8, 640, 1, True, None), (2, 4, 608, 3, False, [608, 540]), (2, 4, 512, 4, False, None),
 ])
 def test_one_pass_backward_matches_oracle_and_two_pass(monkeypatch, B, H, L, window, cls, lengths):
     sv = _sv()
