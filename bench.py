@@ -64,6 +64,7 @@ def parse():
     ap.add_argument('--seq', type=int, default=None)
     ap.add_argument('--profile-steps', type=int, default=3, help='extra, separately timed steps with per-kernel events')
     ap.add_argument('--no-bottleneck-leg', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step kernel by kernel instead of one CUDA-graph replay')
     ap.add_argument('--kernel-only', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-seqs', type=int, default=1)
@@ -82,6 +83,7 @@ def workload_config(args, world):
                     f'batch {args.batch} x seq {args.seq} per GPU, bf16 autocast, RAdam + grad clip',
         'global_batch': args.batch * world, 'seq_len': args.seq, 'parallelism': f'dp{world}',
         'accumulate_grad_batches': 1, 'grad_checkpointing': False,
+        'launch': 'eager, kernel by kernel' if getattr(args, 'no_graph', False) else 'one CUDA-graph replay per step (captured after 2 eager steps)',
         'host_syncs': 'none inside a step (validate_args=False on the returned posterior Normal; the reference checks it on the host)',
         'l2': 'no explicit flush: one step streams >10 GB of activations/weights/gradients through the 126 MB L2',
         'e2e_loss_read': 'every step: async D2H of the loss into pinned memory + event, read by the host one step later',
@@ -452,17 +454,12 @@ def main_ours(args):
     resident = [to_device(hb, dev, non_blocking=False) for hb in host]
     torch.manual_seed(7295 + rank)                           # per-rank dropout / eps streams
 
-    def step(batch):
-        reducer.zero_grad()
-        with torch.autocast('cuda', dtype=torch.bfloat16):
-            out = model.training_step(batch, 0)
-        out['loss'].backward()
-        reducer.finish()
-        model.on_after_backward()                            # gradient clipping (after the all-reduce)
-        opt.step()
-        sched.step()
-        model.global_step += 1
-        return out['loss']
+    # forward + backward + all-reduce + clipping + RAdam: launched kernel by kernel for the first warm-up steps, then
+    # captured once and replayed as ONE CUDA graph per step (core/graph_step.py)
+    from sparse_vae_b200.core.graph_step import GraphedTrainStep
+    graphed = GraphedTrainStep(model, opt, sched, reducer, torch.bfloat16, warmup=2)
+    use_graph = not args.no_graph
+    step = graphed if use_graph else graphed.eager
 
     def barrier():
         if world > 1:
@@ -482,7 +479,7 @@ def main_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3 if use_graph else 0)):
         step(resident[i % n_host])
 
     # ---- device-resident inputs: the headline `value`
@@ -519,7 +516,7 @@ def main_ours(args):
     #      records are outside both headline regions above
     psteps = max(1, args.profile_steps)
     N.profile_begin()
-    timed(lambda i: step(resident[i % n_host]), psteps)
+    timed(lambda i: graphed.eager(resident[i % n_host]), psteps)      # eager: a graph replay runs no host code to time
     prof = N.profile_end()
 
     if rank == 0:
@@ -541,7 +538,8 @@ def main_ours(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'roofline': roof, 'rooflines': rooflines, 'attention': attention,
-            'bottleneck': bottleneck, 'kernels': per_kernel, 'kernels_from': f'{psteps} extra step(s) after the timed regions',
+            'bottleneck': bottleneck, 'kernels': per_kernel,
+            'kernels_from': f'{psteps} extra EAGER step(s) after the timed regions (event pair around every library launch)',
             'cpu_baseline': cpu, 'clocks': clocks,
             'final_loss': losses[-1] if losses else None,
             'grad_allreduce_numel': reducer.reduced_numel,

@@ -181,6 +181,30 @@ SVAE_API int svae_radam_step(int32_t n, void* const* params, void* const* grads,
                     void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
 
+/* ---- CUDA-graph variants (core/graph_step.py): a captured training step is replayed with NEW random numbers and NEW
+ * optimizer scalars each time, so these read them from device memory the host refreshes before every replay.
+ * philox_dev -> {seed, base offset} (uint64[2]); the `offset` argument is then the launch's fixed increment over the base
+ * (the position of this draw inside the step), exactly torch's own offset_intragraph scheme.  NULL = the plain call. */
+SVAE_API int svae_bottleneck_fwd_g(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts, int64_t rows,
+                          int32_t latent, uint64_t seed, uint64_t offset, const uint64_t* philox_dev, int32_t sm_count,
+                          int32_t max_threads_per_sm, float* z, float* sigma, float* kl_elem, float* raw_kl, float* kl,
+                          void* workspace, void* stream);
+SVAE_API int svae_bottleneck_bwd_g(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts, int64_t rows,
+                          int32_t latent, uint64_t seed, uint64_t offset, const uint64_t* philox_dev, int32_t sm_count,
+                          int32_t max_threads_per_sm, const float* dz, const float* dsigma, const float* dkl_elem,
+                          const float* draw_kl, const float* dkl, void* d_mulogvar, int64_t ld_out, void* stream);
+SVAE_API int svae_residual_dropout_add_g(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, float p,
+                                uint64_t seed, uint64_t offset, const uint64_t* philox_dev, void* stream);
+SVAE_API int svae_dropout_branch_grad_g(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
+                               uint64_t offset, const uint64_t* philox_dev, void* stream);
+/* The scalars of one RAdam step as the opaque block svae_radam_step_g reads from DEVICE memory (args_dev): the host
+ * evaluates them with svae_radam_args (same double-precision schedule as svae_radam_step) into a pinned buffer of
+ * svae_radam_args_bytes() bytes and copies it to the device before the replay. */
+SVAE_API int32_t svae_radam_args_bytes(void);
+SVAE_API int svae_radam_args(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* args_out);
+SVAE_API int svae_radam_step_g(int32_t n, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                      const int64_t* numel, const void* args_dev, void* stream);
+
 /* ---- LayerNorm of the pre-LN decoder blocks (reference core/transformer_layer.py:17-24) ---- */
 /* x: [rows, n] contiguous (x_dtype), n in {128, 256, 512, 1024}; gamma/beta fp32 [n] (beta may be NULL).
  * y = (x - mean) * rstd * gamma + beta written in y_dtype (fp32 statistics; a 16-bit y equals the rounded fp32

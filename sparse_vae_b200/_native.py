@@ -42,7 +42,8 @@ EXPORTS = (
     'svae_layernorm_supported', 'svae_layernorm_fwd', 'svae_layernorm_bwd_workspace_floats', 'svae_layernorm_bwd',
     'svae_decode_attn_supported', 'svae_decode_attn', 'svae_sample_top_p_supported', 'svae_sample_top_p',
     'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast', 'svae_residual_dropout_add',
-    'svae_dropout_branch_grad',
+    'svae_dropout_branch_grad', 'svae_bottleneck_fwd_g', 'svae_bottleneck_bwd_g', 'svae_residual_dropout_add_g',
+    'svae_dropout_branch_grad_g', 'svae_radam_args_bytes', 'svae_radam_args', 'svae_radam_step_g',
 )
 
 
@@ -140,6 +141,20 @@ def _load() -> C.CDLL:
     lib.svae_residual_dropout_add.argtypes = [vp, vp, i32, vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
     lib.svae_dropout_branch_grad.restype = C.c_int
     lib.svae_dropout_branch_grad.argtypes = [vp, vp, i32, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
+    lib.svae_bottleneck_fwd_g.restype = C.c_int
+    lib.svae_bottleneck_fwd_g.argtypes = [vp, i64, i32, vp, i64, i32, u64, u64, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.svae_bottleneck_bwd_g.restype = C.c_int
+    lib.svae_bottleneck_bwd_g.argtypes = [vp, i64, i32, vp, i64, i32, u64, u64, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.svae_residual_dropout_add_g.restype = C.c_int
+    lib.svae_residual_dropout_add_g.argtypes = [vp, vp, i32, vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp, vp]
+    lib.svae_dropout_branch_grad_g.restype = C.c_int
+    lib.svae_dropout_branch_grad_g.argtypes = [vp, vp, i32, i64, C.c_float, C.c_uint64, C.c_uint64, vp, vp]
+    lib.svae_radam_args_bytes.restype = i32
+    lib.svae_radam_args_bytes.argtypes = []
+    lib.svae_radam_args.restype = C.c_int
+    lib.svae_radam_args.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp]
+    lib.svae_radam_step_g.restype = C.c_int
+    lib.svae_radam_step_g.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp]
     lib.svae_residual_add.restype = C.c_int
     lib.svae_residual_add.argtypes = [vp, vp, i32, vp, i64, vp]
     lib.svae_residual_layernorm.restype = C.c_int

@@ -34,11 +34,18 @@ def _device_geometry(device: torch.device):
 def philox_reserve(device: torch.device, rows: int, latent: int, generator: Optional[torch.Generator] = None):
     """Takes (seed, offset) from the CUDA generator and advances it exactly as `normal_()` on a
     [rows*latent] tensor would (ATen calc_execution_policy), so later draws stay in step with the reference."""
+    sms, tpm = _device_geometry(device)
+    increment = int(N.lib.svae_bottleneck_philox_increment(rows, latent, sms, tpm))
+    from .graph_step import StepPhilox
+    if StepPhilox.active is not None and generator is None:
+        # a training step is being captured: {seed, base offset} are read from device memory at replay time and this
+        # draw sits `delta` past the base (third element: the device pointer)
+        philox_dev, delta = StepPhilox.active.reserve(increment)
+        return 0, delta, philox_dev
     gen = generator if generator is not None else torch.cuda.default_generators[
         device.index if device.index is not None else torch.cuda.current_device()]
-    sms, tpm = _device_geometry(device)
     seed, offset = gen.initial_seed(), gen.get_offset()
-    gen.set_offset(offset + int(N.lib.svae_bottleneck_philox_increment(rows, latent, sms, tpm)))
+    gen.set_offset(offset + increment)
     return seed, offset
 
 
@@ -46,7 +53,7 @@ class _BottleneckFn(torch.autograd.Function):
     """(mulogvar[rows, 2D], counts[rows]) -> z, sigma, kl_elem [rows, D] fp32, raw_kl[rows], kl[] (mean of raw_kl/counts)."""
 
     @staticmethod
-    def forward(ctx, mulogvar: Tensor, counts: Tensor, seed: int, offset: int):
+    def forward(ctx, mulogvar: Tensor, counts: Tensor, seed: int, offset: int, philox_dev: int = 0):
         if not mulogvar.is_cuda:
             raise ValueError("Only GPU devices are supported for now")
         rows, two_d = mulogvar.shape
@@ -60,12 +67,12 @@ class _BottleneckFn(torch.autograd.Function):
         raw_kl = torch.empty(rows, dtype=torch.float32, device=dev)
         kl = torch.empty((), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            N.check(N.lib.svae_bottleneck_fwd(
+            N.check(N.lib.svae_bottleneck_fwd_g(
                 N.ptr(mulogvar), mulogvar.stride(0), N.svae_dtype(mulogvar.dtype), N.ptr(counts), rows, D, seed, offset,
-                sms, tpm, N.ptr(z), N.ptr(sigma), N.ptr(kl_elem), N.ptr(raw_kl), N.ptr(kl), N.ptr(_workspace(dev)),
+                philox_dev, sms, tpm, N.ptr(z), N.ptr(sigma), N.ptr(kl_elem), N.ptr(raw_kl), N.ptr(kl), N.ptr(_workspace(dev)),
                 N.current_stream(dev)), 'svae_bottleneck_fwd')
         ctx.save_for_backward(mulogvar, counts)
-        ctx.philox = (seed, offset)
+        ctx.philox = (seed, offset, philox_dev)
         return z, sigma, kl_elem, raw_kl, kl
 
     @staticmethod
@@ -75,7 +82,7 @@ class _BottleneckFn(torch.autograd.Function):
         D = two_d // 2
         dev = mulogvar.device
         sms, tpm = _device_geometry(dev)
-        seed, offset = ctx.philox
+        seed, offset, philox_dev = ctx.philox
 
         def f32(t):
             return None if t is None else t.to(torch.float32).contiguous()
@@ -83,11 +90,11 @@ class _BottleneckFn(torch.autograd.Function):
         dz, dsigma, dkl_elem, draw_kl, dkl = map(f32, (dz, dsigma, dkl_elem, draw_kl, dkl))
         grad = torch.empty(rows, two_d, dtype=mulogvar.dtype, device=dev)
         with torch.cuda.device(dev):
-            N.check(N.lib.svae_bottleneck_bwd(
+            N.check(N.lib.svae_bottleneck_bwd_g(
                 N.ptr(mulogvar), mulogvar.stride(0), N.svae_dtype(mulogvar.dtype), N.ptr(counts), rows, D, seed, offset,
-                sms, tpm, N.ptr(dz), N.ptr(dsigma), N.ptr(dkl_elem), N.ptr(draw_kl), N.ptr(dkl), N.ptr(grad),
+                philox_dev, sms, tpm, N.ptr(dz), N.ptr(dsigma), N.ptr(dkl_elem), N.ptr(draw_kl), N.ptr(dkl), N.ptr(grad),
                 grad.stride(0), N.current_stream(dev)), 'svae_bottleneck_bwd')
-        return grad, None, None, None
+        return grad, None, None, None, None
 
 
 def fused_bottleneck(mulogvar: Tensor, token_counts: Optional[Tensor], philox: Optional[Tuple[int, int]] = None,
@@ -113,8 +120,8 @@ def fused_bottleneck(mulogvar: Tensor, token_counts: Optional[Tensor], philox: O
         if per_batch > 1:
             counts = counts.repeat_interleave(per_batch)
         counts = counts.contiguous()
-    seed, offset = philox if philox is not None else philox_reserve(mulogvar.device, rows, D, generator)
-    z, sigma, kl_elem, raw_kl, kl = _BottleneckFn.apply(flat, counts, seed, offset)
+    ph = philox if philox is not None else philox_reserve(mulogvar.device, rows, D, generator)
+    z, sigma, kl_elem, raw_kl, kl = _BottleneckFn.apply(flat, counts, *ph)
     if per_batch > 1:
         raw_kl = raw_kl.reshape(B, per_batch).sum(dim=-1)
         kl = kl * per_batch

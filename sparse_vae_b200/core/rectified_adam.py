@@ -67,7 +67,9 @@ class RAdam(Optimizer):
                 fused = cache.get(id(group))
                 if fused is None:
                     fused = cache[id(group)] = FusedRAdamStep()
-                fused(params, grads, m, v, group['lr'], beta1, beta2, group['eps'], group['weight_decay'], step)
+                from .graph_step import StepOptimArgs
+                args_dev = StepOptimArgs.active.block_for(group) if StepOptimArgs.active is not None else 0
+                fused(params, grads, m, v, group['lr'], beta1, beta2, group['eps'], group['weight_decay'], step, args_dev)
                 group['step'] += 1
                 continue
 

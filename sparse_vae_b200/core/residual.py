@@ -38,23 +38,23 @@ class _ResidualDropoutAddFn(torch.autograd.Function):
     """x + dropout(h) in one launch; the keep mask is regenerated from (seed, offset) in backward, never stored."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, h: Tensor, p: float, seed: int, offset: int):
+    def forward(ctx, x: Tensor, h: Tensor, p: float, seed: int, offset: int, philox_dev: int):
         out = torch.empty_like(x)
-        N.check(N.lib.svae_residual_dropout_add(x.data_ptr(), h.data_ptr(), N.svae_dtype(h.dtype), out.data_ptr(), x.numel(),
-                                                p, seed, offset, N.current_stream(x.device)), 'svae_residual_dropout_add')
-        ctx.args = (p, seed, offset, h.dtype)
+        N.check(N.lib.svae_residual_dropout_add_g(x.data_ptr(), h.data_ptr(), N.svae_dtype(h.dtype), out.data_ptr(), x.numel(),
+                                                  p, seed, offset, philox_dev, N.current_stream(x.device)), 'svae_residual_dropout_add')
+        ctx.args = (p, seed, offset, philox_dev, h.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        p, seed, offset, h_dtype = ctx.args
+        p, seed, offset, philox_dev, h_dtype = ctx.args
         dh = None
         if ctx.needs_input_grad[1]:
             g32 = g.contiguous()
             dh = torch.empty(g32.shape, dtype=h_dtype, device=g32.device)
-            N.check(N.lib.svae_dropout_branch_grad(g32.data_ptr(), dh.data_ptr(), N.svae_dtype(h_dtype), g32.numel(), p, seed,
-                                                   offset, N.current_stream(g32.device)), 'svae_dropout_branch_grad')
-        return (g if ctx.needs_input_grad[0] else None), dh, None, None, None
+            N.check(N.lib.svae_dropout_branch_grad_g(g32.data_ptr(), dh.data_ptr(), N.svae_dtype(h_dtype), g32.numel(), p, seed,
+                                                     offset, philox_dev, N.current_stream(g32.device)), 'svae_dropout_branch_grad')
+        return (g if ctx.needs_input_grad[0] else None), dh, None, None, None, None
 
 
 def residual_dropout_add(x: Tensor, h: Tensor, dropout: torch.nn.Dropout) -> Tensor:
@@ -64,9 +64,14 @@ def residual_dropout_add(x: Tensor, h: Tensor, dropout: torch.nn.Dropout) -> Ten
     if (dropout.training and 0.0 < dropout.p < 1.0 and not dropout.inplace and N.FUSED_EXTRAS and x.is_cuda
             and x.dtype == torch.float32 and h.dtype in (torch.bfloat16, torch.float16) and x.shape == h.shape
             and x.numel() > 0 and x.numel() % 8 == 0 and x.is_contiguous() and h.is_contiguous()
-            and x.data_ptr() % 16 == 0 and h.data_ptr() % 16 == 0 and not torch.cuda.is_current_stream_capturing()):
-        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
-        seed, offset = gen.initial_seed(), gen.get_offset()
-        gen.set_offset(offset + 4)
-        return _ResidualDropoutAddFn.apply(x, h, float(dropout.p), seed, offset)
+            and x.data_ptr() % 16 == 0 and h.data_ptr() % 16 == 0):
+        from .graph_step import StepPhilox
+        if StepPhilox.active is not None:          # a step is being captured: {seed, base offset} are read on the device
+            philox_dev, delta = StepPhilox.active.reserve(4)
+            return _ResidualDropoutAddFn.apply(x, h, float(dropout.p), 0, delta, philox_dev)
+        if not torch.cuda.is_current_stream_capturing():
+            gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+            seed, offset = gen.initial_seed(), gen.get_offset()
+            gen.set_offset(offset + 4)
+            return _ResidualDropoutAddFn.apply(x, h, float(dropout.p), seed, offset, 0)
     return residual_add(x, dropout(h))

@@ -29,7 +29,13 @@ constexpr int kBnPartialOffset = 64;
 struct PhiloxPlan {
   uint64_t seed, offset;
   int64_t T;   // threads of the emulated ATen launch = 256 * grid
+  const uint64_t* dev;   // non-null (CUDA-graph replay): seed = dev[0], offset = dev[1] + offset, read on the device
 };
+
+__device__ __forceinline__ PhiloxPlan resolve(PhiloxPlan pp) {
+  if (pp.dev) { pp.seed = pp.dev[0]; pp.offset += pp.dev[1]; }
+  return pp;
+}
 
 __host__ inline int64_t aten_grid(int64_t numel, int sm_count, int max_threads_per_sm) {
   int64_t grid = (numel + 255) / 256;
@@ -94,6 +100,7 @@ __device__ __forceinline__ void quad_rows(int64_t q, int64_t rows, int64_t R, in
 
 template <typename T, bool SHARE>
 __global__ void __launch_bounds__(kBnThreads) bottleneck_fwd_kernel(BnFwdArgs a) {
+  a.pp = resolve(a.pp);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = kBnThreads / 32;
   const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(kBnThreads) bottleneck_fwd_kernel(BnFwdArgs a)
 
 template <typename T, bool SHARE>
 __global__ void __launch_bounds__(kBnThreads) bottleneck_bwd_kernel(BnBwdArgs a) {
+  a.pp = resolve(a.pp);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = kBnThreads / 32;
   const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
@@ -277,6 +285,7 @@ __device__ __forceinline__ float comp4(const float4& v, int j) { return j == 0 ?
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, SVAE_BN_VEC_BLOCKS) bottleneck_fwd_vec_kernel(BnFwdArgs a) {
+  a.pp = resolve(a.pp);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = kBnThreads / 32;
   const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(kBnThreads, SVAE_BN_VEC_BLOCKS) bottleneck_fwd
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, SVAE_BN_VEC_BLOCKS) bottleneck_bwd_vec_kernel(BnBwdArgs a) {
+  a.pp = resolve(a.pp);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = kBnThreads / 32;
   const T* __restrict__ in = reinterpret_cast<const T*>(a.mulogvar);
@@ -432,6 +442,7 @@ static int make_plan(int64_t rows, int latent, uint64_t seed, uint64_t offset, i
   p->pp.seed = seed;
   p->pp.offset = offset;
   p->pp.T = T;
+  p->pp.dev = nullptr;
   p->share = (T % latent == 0);
 #ifdef SVAE_BN_NO_VEC
   p->vec = false;
@@ -464,10 +475,10 @@ extern "C" uint64_t svae_bottleneck_philox_increment(int64_t rows, int32_t laten
   return (uint64_t)(((numel - 1) / (256 * grid * 4) + 1) * 4);
 }
 
-extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
-                                   int64_t rows, int32_t latent, uint64_t seed, uint64_t offset, int32_t sm_count,
-                                   int32_t max_threads_per_sm, float* z, float* sigma, float* kl_elem, float* raw_kl,
-                                   float* kl, void* workspace, void* stream) {
+extern "C" int svae_bottleneck_fwd_g(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+                                     int64_t rows, int32_t latent, uint64_t seed, uint64_t offset, const uint64_t* philox_dev,
+                                     int32_t sm_count, int32_t max_threads_per_sm, float* z, float* sigma, float* kl_elem,
+                                     float* raw_kl, float* kl, void* workspace, void* stream) {
   SVAE_REQUIRE(mulogvar && token_counts && z && sigma && raw_kl && kl && workspace, SVAE_ERR_INVALID,
                "svae_bottleneck_fwd: null pointer argument");
   SVAE_REQUIRE(ld >= 2 * (int64_t)latent, SVAE_ERR_INVALID, "svae_bottleneck_fwd: ld (%lld) < 2*latent (%d)",
@@ -475,6 +486,7 @@ extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dty
   BnPlan p;
   int rc = make_plan(rows, latent, seed, offset, sm_count, max_threads_per_sm, &p);
   if (rc) return rc;
+  p.pp.dev = philox_dev;
   BnFwdArgs a{mulogvar, ld, token_counts, rows, latent, p.pp, z, sigma, kl_elem, raw_kl, kl,
               reinterpret_cast<float*>(workspace), p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -501,17 +513,26 @@ extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dty
   return SVAE_OK;
 }
 
-extern "C" int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+extern "C" int svae_bottleneck_fwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
                                    int64_t rows, int32_t latent, uint64_t seed, uint64_t offset, int32_t sm_count,
-                                   int32_t max_threads_per_sm, const float* dz, const float* dsigma,
-                                   const float* dkl_elem, const float* draw_kl, const float* dkl, void* d_mulogvar,
-                                   int64_t ld_out, void* stream) {
+                                   int32_t max_threads_per_sm, float* z, float* sigma, float* kl_elem, float* raw_kl,
+                                   float* kl, void* workspace, void* stream) {
+  return svae_bottleneck_fwd_g(mulogvar, ld, dtype, token_counts, rows, latent, seed, offset, nullptr, sm_count, max_threads_per_sm, z,
+                               sigma, kl_elem, raw_kl, kl, workspace, stream);
+}
+
+extern "C" int svae_bottleneck_bwd_g(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+                                     int64_t rows, int32_t latent, uint64_t seed, uint64_t offset, const uint64_t* philox_dev,
+                                     int32_t sm_count, int32_t max_threads_per_sm, const float* dz, const float* dsigma,
+                                     const float* dkl_elem, const float* draw_kl, const float* dkl, void* d_mulogvar,
+                                     int64_t ld_out, void* stream) {
   SVAE_REQUIRE(mulogvar && token_counts && d_mulogvar, SVAE_ERR_INVALID, "svae_bottleneck_bwd: null pointer argument");
   SVAE_REQUIRE(ld >= 2 * (int64_t)latent && ld_out >= 2 * (int64_t)latent, SVAE_ERR_INVALID,
                "svae_bottleneck_bwd: leading dimension smaller than 2*latent");
   BnPlan p;
   int rc = make_plan(rows, latent, seed, offset, sm_count, max_threads_per_sm, &p);
   if (rc) return rc;
+  p.pp.dev = philox_dev;
   BnBwdArgs a{mulogvar, ld, token_counts, rows, latent, p.pp, dz, dsigma, dkl_elem, draw_kl, dkl, d_mulogvar, ld_out,
               p.quads, p.rows_per_T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -535,4 +556,13 @@ extern "C" int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dty
 #undef SVAE_BN_LAUNCH
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
+}
+
+extern "C" int svae_bottleneck_bwd(const void* mulogvar, int64_t ld, int32_t dtype, const int64_t* token_counts,
+                                   int64_t rows, int32_t latent, uint64_t seed, uint64_t offset, int32_t sm_count,
+                                   int32_t max_threads_per_sm, const float* dz, const float* dsigma,
+                                   const float* dkl_elem, const float* draw_kl, const float* dkl, void* d_mulogvar,
+                                   int64_t ld_out, void* stream) {
+  return svae_bottleneck_bwd_g(mulogvar, ld, dtype, token_counts, rows, latent, seed, offset, nullptr, sm_count, max_threads_per_sm, dz,
+                               dsigma, dkl_elem, draw_kl, dkl, d_mulogvar, ld_out, stream);
 }

@@ -46,7 +46,9 @@ __device__ __forceinline__ void radam_one(float& p, float g, float& m, float& v,
   }
 }
 
-__global__ void __launch_bounds__(kMtThreads) radam_kernel(const __grid_constant__ MtTable<4> t, const RadamArgs a) {
+__global__ void __launch_bounds__(kMtThreads) radam_kernel(const __grid_constant__ MtTable<4> t, const RadamArgs a_host,
+                                                             const RadamArgs* __restrict__ a_dev) {
+  const RadamArgs a = a_dev ? *a_dev : a_host;        // graph replay: the step's scalars are read from device memory
   const int ti = t.block_tensor[blockIdx.x];
   const int64_t base = (int64_t)t.block_chunk[blockIdx.x] * kMtChunk;
   const int64_t n = t.numel[ti];
@@ -293,13 +295,8 @@ extern "C" int svae_clip_grad_norm(int32_t n, void* const* grads, const int64_t*
   return rc;
 }
 
-extern "C" int svae_radam_step(int32_t n, void* const* params, void* const* grads, void* const* exp_avg,
-                               void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
-                               double weight_decay, int64_t step, void* stream) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  SVAE_REQUIRE(n >= 0 && params && grads && exp_avg && exp_avg_sq && numel, SVAE_ERR_INVALID, "svae_radam_step: null argument");
-  SVAE_REQUIRE(step >= 1, SVAE_ERR_INVALID, "svae_radam_step: step is 1-indexed");
-  // scalar schedule in double precision, exactly the reference's Python arithmetic (core/rectified_adam.py:24-36,72)
+// scalar schedule in double precision, exactly the reference's Python arithmetic (core/rectified_adam.py:24-36,72)
+static RadamArgs radam_args(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step) {
   const double b1 = beta1, b2 = beta2;
   const double beta2_t = pow(b2, (double)step);
   const double bias_v = sqrt(1.0 - beta2_t);
@@ -318,11 +315,43 @@ extern "C" int svae_radam_step(int32_t n, void* const* params, void* const* grad
   a.decay = (float)(1.0 - lr_eff * weight_decay);
   a.step_size = (float)(lr_eff / bias_m);
   a.bias_v = (float)bias_v;
+  return a;
+}
+
+extern "C" int32_t svae_radam_args_bytes(void) { return (int32_t)sizeof(RadamArgs); }
+
+extern "C" int svae_radam_args(double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                               void* args_out) {
+  SVAE_REQUIRE(args_out && step >= 1, SVAE_ERR_INVALID, "svae_radam_args: null output or step < 1");
+  *reinterpret_cast<RadamArgs*>(args_out) = radam_args(lr, beta1, beta2, eps, weight_decay, step);
+  return SVAE_OK;
+}
+
+static int radam_launch(int32_t n, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                        const int64_t* numel, const RadamArgs& a, const RadamArgs* a_dev, cudaStream_t st) {
   void* const* lists[4] = {params, grads, exp_avg, exp_avg_sq};
   ScopedKernelTimer timer("radam_step", st);
   return for_each_table<4>(n, lists, numel, [&](const MtTable<4>& t, int nb, int) -> int {
-    radam_kernel<<<nb, kMtThreads, 0, st>>>(t, a);
+    radam_kernel<<<nb, kMtThreads, 0, st>>>(t, a, a_dev);
     SVAE_CUDA_CHECK(cudaGetLastError());
     return SVAE_OK;
   });
+}
+
+extern "C" int svae_radam_step(int32_t n, void* const* params, void* const* grads, void* const* exp_avg,
+                               void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, int64_t step, void* stream) {
+  SVAE_REQUIRE(n >= 0 && params && grads && exp_avg && exp_avg_sq && numel, SVAE_ERR_INVALID, "svae_radam_step: null argument");
+  SVAE_REQUIRE(step >= 1, SVAE_ERR_INVALID, "svae_radam_step: step is 1-indexed");
+  return radam_launch(n, params, grads, exp_avg, exp_avg_sq, numel, radam_args(lr, beta1, beta2, eps, weight_decay, step), nullptr,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svae_radam_step_g(int32_t n, void* const* params, void* const* grads, void* const* exp_avg,
+                                 void* const* exp_avg_sq, const int64_t* numel, const void* args_dev, void* stream) {
+  SVAE_REQUIRE(n >= 0 && params && grads && exp_avg && exp_avg_sq && numel && args_dev, SVAE_ERR_INVALID,
+               "svae_radam_step_g: null argument");
+  RadamArgs unused{};
+  return radam_launch(n, params, grads, exp_avg, exp_avg_sq, numel, unused, reinterpret_cast<const RadamArgs*>(args_dev),
+                      reinterpret_cast<cudaStream_t>(stream));
 }

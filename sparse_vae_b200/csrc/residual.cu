@@ -72,7 +72,9 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
 template <typename T>
 __global__ void __launch_bounds__(256) residual_dropout_add_kernel(const float* __restrict__ x, const T* __restrict__ h,
                                                                     float* __restrict__ out, int64_t vecs, unsigned threshold,
-                                                                    float scale, uint64_t seed, uint64_t offset) {
+                                                                    float scale, uint64_t seed, uint64_t offset,
+                                                                    const uint64_t* __restrict__ philox_dev) {
+  if (philox_dev) { seed = philox_dev[0]; offset += philox_dev[1]; }      // graph replay: (seed, base offset) live on the device
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(x + i * 8), b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
     float f[8];
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(256) residual_dropout_add_kernel(const float* 
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_branch_grad_kernel(const float* __restrict__ g, T* __restrict__ dh, int64_t vecs,
                                                                    unsigned threshold, float scale, uint64_t seed,
-                                                                   uint64_t offset) {
+                                                                   uint64_t offset, const uint64_t* __restrict__ philox_dev) {
+  if (philox_dev) { seed = philox_dev[0]; offset += philox_dev[1]; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecs; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(g + i * 8), b = *reinterpret_cast<const float4*>(g + i * 8 + 4);
     float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -124,8 +127,8 @@ static unsigned dropout_threshold(float p) {
   return t >= 4294967295.0 ? 4294967295u : (unsigned)t;
 }
 
-extern "C" int svae_residual_dropout_add(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, float p,
-                                         uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int svae_residual_dropout_add_g(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, float p,
+                                           uint64_t seed, uint64_t offset, const uint64_t* philox_dev, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = residual_dropout_common(x, h, out, h_dtype, numel, p, "svae_residual_dropout_add")) return rc;
   if (numel == 0) return SVAE_OK;
@@ -136,16 +139,21 @@ extern "C" int svae_residual_dropout_add(const float* x, const void* h, int32_t 
   const float scale = 1.0f / (1.0f - p);
   if (h_dtype == SVAE_DTYPE_BF16)
     residual_dropout_add_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(x, (const __nv_bfloat16*)h, out, vecs,
-                                                                               dropout_threshold(p), scale, seed, offset);
+                                                                               dropout_threshold(p), scale, seed, offset, philox_dev);
   else
     residual_dropout_add_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(x, (const __half*)h, out, vecs, dropout_threshold(p),
-                                                                        scale, seed, offset);
+                                                                        scale, seed, offset, philox_dev);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
 
-extern "C" int svae_dropout_branch_grad(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
-                                        uint64_t offset, void* stream) {
+extern "C" int svae_residual_dropout_add(const float* x, const void* h, int32_t h_dtype, float* out, int64_t numel, float p,
+                                         uint64_t seed, uint64_t offset, void* stream) {
+  return svae_residual_dropout_add_g(x, h, h_dtype, out, numel, p, seed, offset, nullptr, stream);
+}
+
+extern "C" int svae_dropout_branch_grad_g(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
+                                          uint64_t offset, const uint64_t* philox_dev, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = residual_dropout_common(g, dh, dh, h_dtype, numel, p, "svae_dropout_branch_grad")) return rc;
   if (numel == 0) return SVAE_OK;
@@ -156,10 +164,10 @@ extern "C" int svae_dropout_branch_grad(const float* g, void* dh, int32_t h_dtyp
   const float scale = 1.0f / (1.0f - p);
   if (h_dtype == SVAE_DTYPE_BF16)
     dropout_branch_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(g, (__nv_bfloat16*)dh, vecs, dropout_threshold(p),
-                                                                              scale, seed, offset);
+                                                                              scale, seed, offset, philox_dev);
   else
     dropout_branch_grad_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(g, (__half*)dh, vecs, dropout_threshold(p), scale, seed,
-                                                                       offset);
+                                                                       offset, philox_dev);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
@@ -184,4 +192,9 @@ extern "C" int svae_residual_add(const float* x, const void* h, int32_t h_dtype,
     residual_add_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(x, (const __half*)h, out, vecs);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
+}
+
+extern "C" int svae_dropout_branch_grad(const float* g, void* dh, int32_t h_dtype, int64_t numel, float p, uint64_t seed,
+                                        uint64_t offset, void* stream) {
+  return svae_dropout_branch_grad_g(g, dh, h_dtype, numel, p, seed, offset, nullptr, stream);
 }

@@ -72,15 +72,19 @@ class FusedRAdamStep:
         self._p, self._g, self._m, self._v = _PtrList(), _PtrList(), _PtrList(), _PtrList()
 
     def __call__(self, params: List[Tensor], grads: List[Tensor], exp_avg: List[Tensor], exp_avg_sq: List[Tensor],
-                 lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int):
+                 lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int, args_dev: int = 0):
         _check_fp32_cuda(params, 'RAdam params')
         _check_fp32_cuda(grads, 'RAdam grads')
         dev = params[0].device
         p, g = self._p.update(params), self._g.update(grads)
         m, v = self._m.update(exp_avg), self._v.update(exp_avg_sq)
-        N.check(N.lib.svae_radam_step(p.n, p.ptrs, g.ptrs, m.ptrs, v.ptrs, p.numel, float(lr), float(beta1), float(beta2),
-                                      float(eps), float(weight_decay), int(step), N.current_stream(dev)),
-                'svae_radam_step')
+        if args_dev:        # a captured step: the scalars are read from device memory at replay time (core/graph_step.py)
+            N.check(N.lib.svae_radam_step_g(p.n, p.ptrs, g.ptrs, m.ptrs, v.ptrs, p.numel, args_dev, N.current_stream(dev)),
+                    'svae_radam_step_g')
+        else:
+            N.check(N.lib.svae_radam_step(p.n, p.ptrs, g.ptrs, m.ptrs, v.ptrs, p.numel, float(lr), float(beta1), float(beta2),
+                                          float(eps), float(weight_decay), int(step), N.current_stream(dev)),
+                    'svae_radam_step')
         # the kernel wrote through raw pointers: tell autograd (and anything keyed on tensor versions) about it
         torch.autograd.graph.increment_version(params)
 
