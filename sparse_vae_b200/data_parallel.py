@@ -145,6 +145,38 @@ class GradientAllReducer:
                 b.work = None
             b.pending = len(b.params)
 
+    def reduce_tensors(self, grads_by_param: dict):
+        """All-reduce (mean) of gradients that live OUTSIDE the `.grad` attributes -- the static gradient tensors of a
+        captured backward (core/graph_step.py): packed into the flat buckets (1/world folded in), reduced, waited for;
+        afterwards every `.grad` is the bucket view.  `grads_by_param`: {id(parameter): gradient tensor}."""
+        assert self._built, "run one eager step first: the buckets are laid out after the first backward"
+        for b in self.buckets:
+            dst, src = [], []
+            for v, p in zip(b.views, b.params):
+                g = grads_by_param.get(id(p))
+                if g is None:
+                    v.zero_()
+                else:
+                    dst.append(v)
+                    src.append(g)
+            if dst:
+                if b.flat.is_cuda and all(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in src):
+                    if b._fused is None:
+                        from .fused_optim import FusedScaleCopy
+                        b._fused = FusedScaleCopy()
+                    b._fused(dst, src, 1.0 / self.world)
+                else:
+                    for v, g in zip(dst, src):
+                        v.copy_(g)
+                        v.mul_(1.0 / self.world)
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        for b in self.buckets:
+            b.work.wait()
+            b.work = None
+            b.pending = len(b.params)
+            for v, p in zip(b.views, b.params):
+                p.grad = v
+
     def zero_grad(self):
         self.module.zero_grad(set_to_none=True)
 

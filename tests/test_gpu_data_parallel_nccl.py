@@ -45,19 +45,62 @@ def _model(dev):
 
 def _batch(dev, lo, hi):
     from sparse_vae_b200.synthetic import synthetic_tokens, to_device
-    host = synthetic_tokens(B_GLOBAL, L, seed=11, lengths=[L, L - 37, L - 200, L - 5])
+    # full-length sequences: the NLL is a mean over a rank's own valid tokens, so the mean of the ranks' losses is the
+    # global-batch loss only when every rank holds the same number of them
+    host = synthetic_tokens(B_GLOBAL, L, seed=11)
     host = {k: v[lo:hi] for k, v in host.items()}
     return to_device(host, dev, non_blocking=False)
 
 
 def _step(model, batch, reducer=None):
+    # fp32 end to end (the attention runs its exact fp32 kernels): the comparison is then limited by summation order only,
+    # not by bf16 GEMMs that pick different tilings for 1024 and 2048 rows
     model.zero_grad(set_to_none=True)
-    with torch.autocast('cuda', dtype=torch.bfloat16):
+    with torch.autocast('cuda', enabled=False):
         out = model.training_step(batch, 0)
     out['loss'].backward()
     if reducer is not None:
         reducer.finish()
     return out['loss'].detach().float()
+
+
+def _graph_worker(rank, world, port, out):
+    """Two ranks, the split-graph step (graph A, eager all-reduce, graph B) against the eager step on the same data."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from sparse_vae_b200.core.graph_step import GraphedTrainStep
+    from sparse_vae_b200.data_parallel import GradientAllReducer, init_distributed
+    r, local, w = init_distributed('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    per = B_GLOBAL // world
+    losses = {}
+    for mode in ('eager', 'graph'):
+        model = _model(dev)
+        (opt,), (cfg,) = model.configure_optimizers(tokens_per_batch=B_GLOBAL * L, accumulate_grad_batches=1)
+        reducer = GradientAllReducer(model, bucket_mb=4.0)
+        step = GraphedTrainStep(model, opt, cfg['scheduler'], reducer, torch.bfloat16, warmup=2)
+        fn = step.eager if mode == 'eager' else step
+        torch.manual_seed(99)
+        losses[mode] = [float(fn(_batch(dev, rank * per, (rank + 1) * per))) for _ in range(5)]
+        if mode == 'graph':
+            assert step.graph_b is not None
+        reducer.remove()
+    out[rank] = losses
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_rank_split_graph_step_matches_eager():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    for rank in range(world):
+        for a, b in zip(res[rank]['eager'], res[rank]['graph']):
+            assert abs(a - b) <= 1e-5 * abs(a), res
 
 
 def _worker(rank, world, port, out):
@@ -100,8 +143,6 @@ def test_two_rank_nccl_step_matches_single_process():
         m = multi[0][it]
         assert multi[0][it]['same'] and multi[1][it]['same'], 'ranks disagree bitwise after the all-reduce'
         assert abs(m['loss'] - loss) <= 1e-5 * abs(loss), (m['loss'], loss)
-        assert abs(m['gnorm'] - flat.norm().item()) <= 1e-3 * flat.norm().item(), (m['gnorm'], flat.norm().item())
-        # element-wise: bf16 GEMMs with different batch decompositions round differently; the bound is relative to the
-        # gradient's scale
-        err = (m['grad'] - flat).abs().max().item() / flat.abs().max().item()
-        assert err <= 2e-2, err
+        assert abs(m['gnorm'] - flat.norm().item()) <= 1e-4 * flat.norm().item(), (m['gnorm'], flat.norm().item())
+        err = (m['grad'] - flat).abs().max().item() / flat.abs().max().item()        # relative to the gradient's scale
+        assert err <= 1e-3, err
