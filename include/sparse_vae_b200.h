@@ -181,6 +181,25 @@ SVAE_API int svae_radam_step(int32_t n, void* const* params, void* const* grads,
                     void* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
 
+/* ---- dense attention of a few queries over a long key sequence (the Perceiver encoder's learned-query layers:
+ * reference core/perceiver.py:16-50 -> core/attention.py:83-100; non-causal, additive key padding) ---- */
+typedef struct svae_xattn_desc {
+  int32_t batch, heads, num_queries, num_keys, head_dim;
+  int32_t dtype;          /* SVAE_DTYPE_BF16 / SVAE_DTYPE_F16 */
+  float   scale;          /* head_dim ** -0.5 */
+  int32_t reserved;
+  int64_t q_stride[3], k_stride[3], v_stride[3], o_stride[3];       /* {batch, head, row}, elements; unit inner stride */
+  int64_t do_stride[3], dq_stride[3], dk_stride[3], dv_stride[3];   /* backward only */
+} svae_xattn_desc;
+/* 1 if the tcgen05 kernels apply: 16-bit tensors, head_dim 64, 1..128 queries (backward: <= 64) */
+SVAE_API int svae_xattn_supported(const svae_xattn_desc* desc);
+/* out[b,h,q,:] = softmax_k(scale * q k^T + key_padding_mask[b, k]) v ; lse: fp32 [batch, heads, num_queries] */
+SVAE_API int svae_xattn_fwd(const svae_xattn_desc* desc, const void* q, const void* k, const void* v,
+                   const float* key_padding_mask, void* out, float* lse, void* stream);
+SVAE_API int svae_xattn_bwd(const svae_xattn_desc* desc, const void* q, const void* k, const void* v, const void* out,
+                   const void* dout, const float* lse, const float* key_padding_mask, void* dq, void* dk, void* dv,
+                   void* stream);
+
 /* ---- CUDA-graph variants (core/graph_step.py): a captured training step is replayed with NEW random numbers and NEW
  * optimizer scalars each time, so these read them from device memory the host refreshes before every replay.
  * philox_dev -> {seed, base offset} (uint64[2]); the `offset` argument is then the launch's fixed increment over the base

@@ -44,6 +44,7 @@ EXPORTS = (
     'svae_residual_layernorm', 'svae_residual_add', 'svae_multi_tensor_cast', 'svae_residual_dropout_add',
     'svae_dropout_branch_grad', 'svae_bottleneck_fwd_g', 'svae_bottleneck_bwd_g', 'svae_residual_dropout_add_g',
     'svae_dropout_branch_grad_g', 'svae_radam_args_bytes', 'svae_radam_args', 'svae_radam_step_g',
+    'svae_xattn_supported', 'svae_xattn_fwd', 'svae_xattn_bwd',
 )
 
 

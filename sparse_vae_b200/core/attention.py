@@ -22,6 +22,7 @@ from .. import _native as N
 from .layer_norm import LayerNorm
 from .linear import Linear, linear3
 from .padded_tensor import split_padding
+from . import cross_attention
 from .residual import residual_add, residual_dropout_add
 from .rotary_embedding import RotaryEmbedding
 from .sparse_attention import SparseAttention
@@ -155,6 +156,11 @@ class Attention(nn.Module):
         if sparse and self.key_cache is None:
             kpm = padding * -1e7 if padding is not None else None
             out = sparse(q, k, v, key_padding_mask=kpm)                                 # [B, H, L, Dh] over [B, L, H, Dh]
+        elif (N.FUSED_EXTRAS and not self.causal and self.key_cache is None and (padding is None or padding.ndim == 2)
+              and cross_attention.supported(q, k, v)):
+            # the Perceiver encoder's learned queries (<= 64) over the whole sequence: K and V streamed once through
+            # the tcgen05 kernels of csrc/xattn_sm100.cu; the additive mask is the reference's float32 -1e7
+            out = cross_attention.cross_attention(q, k, v, None if padding is None else padding * -1e7)
         elif (N.FUSED_EXTRAS and q.is_cuda and self.key_cache is None and q.ndim == 4
               and (padding is None or (padding.ndim == 2 and not self.causal))):
             # Dense attention of the Perceiver encoder (64 learned queries over the whole sequence) and of non-sparse
