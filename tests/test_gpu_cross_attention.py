@@ -43,7 +43,7 @@ def test_cross_attention_matches_float64(B, H, nq, Lk, dtype, lengths):
         for b, n in enumerate(lengths):
             pad[b, n:] = True
         kpm = (pad * -1e7).to(dev)
-    assert xa.supported(q, k, v)
+    assert xa.supported(q, k, v) == (B * H >= xa.MIN_PAIRS)
     out = xa.cross_attention(q, k, v, kpm)
     assert out.shape == q.shape and out.dtype == dtype
     out.backward(dout)
