@@ -17,11 +17,12 @@ parameters and read from device memory that the host refreshes right before each
   device memory (`svae_radam_step_g`).
 * the batch: copied into static input tensors.
 
-With more than one process the gradient all-reduce stays OUTSIDE the graphs (an NCCL collective launched from an autograd
-hook inside a capture deadlocked on this stack): graph A = forward + backward into static gradient tensors, then the
-bucketed all-reduce launched eagerly (`GradientAllReducer.reduce_tensors`), then graph B = clipping + RAdam on the
-reduced buckets.  The all-reduce no longer overlaps the backward; at 185 MB over NVLink that costs less than the launch
-gaps it removes.
+With more than one process the NCCL calls stay OUTSIDE the graphs (a collective launched from an autograd hook inside a
+capture deadlocked on this stack) but still overlap the backward: graph A = forward + backward with the reducer's hooks
+live -- each gradient bucket is packed by a captured launch as soon as its last gradient exists, followed by an EXTERNAL
+event-record node -- and right after `graph A.replay()` the host issues the bucket all-reduces on a side stream, each
+behind its bucket's event (`GradientAllReducer.replay_reduce`); graph B = clipping + RAdam on the reduced buckets waits
+for the last of them.  (`SVAE_DP_OVERLAP=0`: pack and reduce after graph A has finished, the first version: +1.7 ms.)
 
 Reference call sites of what is captured: `TransformerVAE.training_step` (transformer_vae.py:42-66),
 `LanguageModel.on_after_backward` (core/language_model.py:120-122), `RAdam.step` (core/rectified_adam.py:15-88).
@@ -29,6 +30,7 @@ Reference call sites of what is captured: `TransformerVAE.training_step` (transf
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -113,6 +115,8 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_b: Optional[torch.cuda.CUDAGraph] = None          # world > 1: clipping + optimizer, after the all-reduce
         self.split = reducer is not None and getattr(reducer, 'world', 1) > 1
+        # world > 1: all-reduce each bucket while the replayed backward is still running (SVAE_DP_OVERLAP=0: after it)
+        self.overlap = self.split and os.environ.get('SVAE_DP_OVERLAP', '1') != '0'
         self._captured_grads = None
         self.static_batch: Optional[Dict[str, torch.Tensor]] = None
         self.static_loss: Optional[torch.Tensor] = None
@@ -173,18 +177,30 @@ class GraphedTrainStep:
                 with torch.cuda.graph(self.graph):
                     self.static_loss = self._device_work(self.static_batch)
             else:
-                self.reducer.sync = False              # the hooks stay quiet: no collective inside the capture
-                try:
+                if self.overlap:
+                    # hooks live: every bucket is packed inside the graph as soon as its last gradient exists and an
+                    # external event marks the spot; the collectives themselves are issued eagerly after the replay
                     with torch.cuda.graph(self.graph):
                         self.reducer.zero_grad()
+                        self.reducer.begin_capture()
                         with torch.autocast('cuda', dtype=self.autocast_dtype):
                             out = self.model.training_step(self.static_batch, 0)
                         out['loss'].backward()
+                        self.reducer.end_capture()     # `.grad` -> bucket views, which graph B reads
                         self.static_loss = out['loss'].detach()
-                finally:
-                    self.reducer.sync = True
-                self._captured_grads = {id(p): p.grad for p in self.model.parameters() if p.grad is not None}
-                self.reducer.reduce_tensors(self._captured_grads)        # `.grad` -> bucket views, which graph B reads
+                else:
+                    self.reducer.sync = False          # the hooks stay quiet: pack + reduce after the replay
+                    try:
+                        with torch.cuda.graph(self.graph):
+                            self.reducer.zero_grad()
+                            with torch.autocast('cuda', dtype=self.autocast_dtype):
+                                out = self.model.training_step(self.static_batch, 0)
+                            out['loss'].backward()
+                            self.static_loss = out['loss'].detach()
+                    finally:
+                        self.reducer.sync = True
+                    self._captured_grads = {id(p): p.grad for p in self.model.parameters() if p.grad is not None}
+                    self.reducer.reduce_tensors(self._captured_grads)    # `.grad` -> bucket views, which graph B reads
                 self.graph_b = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
                     self.model.on_after_backward()
@@ -213,7 +229,10 @@ class GraphedTrainStep:
         self.optim_args.refresh()
         self.graph.replay()
         if self.split:
-            self.reducer.reduce_tensors(self._captured_grads)
+            if self.overlap:
+                self.reducer.replay_reduce()
+            else:
+                self.reducer.reduce_tensors(self._captured_grads)
             self.graph_b.replay()
         self.optim_args.advance()
         self._host_bookkeeping()

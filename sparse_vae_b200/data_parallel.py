@@ -34,6 +34,7 @@ class _Bucket:
         self.pending = len(params)
         self.work = None
         self._fused = None
+        self.event = None           # external event recorded inside a captured backward once the bucket is packed
 
     def gather(self, scale: float):
         """Packs the gradients autograd left on the parameters into the flat buffer (times `scale`) and re-points
@@ -79,6 +80,9 @@ class GradientAllReducer:
         self._built = False
         self._reduced_numel = 0
         self.sync = True        # set False for all but the last micro-batch of a gradient-accumulation step
+        self._capturing = False  # inside a CUDA-graph capture of forward + backward (begin_capture / end_capture)
+        self._capture_order: List[_Bucket] = []
+        self._comm_stream = None
 
     # ---- hooks ----------------------------------------------------------------------------------
     def _on_grad(self, p: nn.Parameter):
@@ -98,6 +102,15 @@ class GradientAllReducer:
         # gradients arrive as separate tensors (autograd assigns them: `.grad` is None at the start of a step, so
         # nothing is zero-filled or accumulated); one launch packs the bucket and applies the 1/world averaging
         b.gather(1.0 / self.world)
+        if self._capturing:
+            # the pack is part of the graph; the collective is NOT (see begin_capture): an event-record node marks the
+            # point of the replayed backward from which the bucket may be reduced
+            if b.event is None:
+                b.event = torch.cuda.Event(external=True)
+            b.event.record()
+            b.work = 'captured'
+            self._capture_order.append(b)
+            return
         b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _build(self):
@@ -144,6 +157,45 @@ class GradientAllReducer:
                 b.work.wait()
                 b.work = None
             b.pending = len(b.params)
+
+    # ---- captured backward: the all-reduce overlaps the replayed graph ---------------------------------------------
+    def begin_capture(self):
+        """Call inside `torch.cuda.graph(...)` before the forward pass.  The hooks stay live during the captured
+        backward: each bucket is packed by a captured launch as soon as its last gradient exists, followed by an
+        EXTERNAL event-record node.  No collective is captured (an NCCL call issued from the autograd thread inside a
+        capture deadlocked on this stack); `replay_reduce()` issues them eagerly on a side stream, each behind its
+        bucket's event, so they run while the rest of the replayed backward is still executing."""
+        assert self._built and self.world > 1, "run one eager step first: the buckets are laid out after the first backward"
+        self._capturing = True
+        self._capture_order = []
+        for b in self.buckets:
+            b.pending, b.work = len(b.params), None
+
+    def end_capture(self):
+        """Call inside the capture after backward(): buckets whose hook never completed (a parameter without a
+        gradient on this step) are packed here, zero-filled where nothing arrived."""
+        for b in self.buckets:
+            if b.work is None:
+                self._launch(b)
+        self._capturing = False
+        for b in self.buckets:
+            b.pending, b.work = len(b.params), None
+
+    def replay_reduce(self):
+        """Right after `graph.replay()` of a backward captured between begin_capture / end_capture: all-reduce every
+        bucket on the communication stream as soon as the replay has packed it; the caller's stream then waits for all
+        of them (clipping and the optimizer read the bucket views, which the `.grad` attributes already are)."""
+        main = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for b in self._capture_order:
+                self._comm_stream.wait_event(b.event)
+                works.append(dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()                          # the caller's stream waits for the collective (no host block)
+        main.wait_stream(self._comm_stream)
 
     def reduce_tensors(self, grads_by_param: dict):
         """All-reduce (mean) of gradients that live OUTSIDE the `.grad` attributes -- the static gradient tensors of a

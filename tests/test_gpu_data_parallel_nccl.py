@@ -65,7 +65,8 @@ def _step(model, batch, reducer=None):
 
 
 def _graph_worker(rank, world, port, out):
-    """Two ranks, the split-graph step (graph A, eager all-reduce, graph B) against the eager step on the same data."""
+    """Two ranks, the split-graph step (graph A, all-reduce behind in-graph events or after the graph, graph B) against
+    the eager step on the same data."""
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     from sparse_vae_b200.core.graph_step import GraphedTrainStep
@@ -75,7 +76,8 @@ def _graph_worker(rank, world, port, out):
     torch.cuda.set_device(dev)
     per = B_GLOBAL // world
     losses = {}
-    for mode in ('eager', 'graph'):
+    for mode in ('eager', 'graph', 'graph_no_overlap'):
+        os.environ['SVAE_DP_OVERLAP'] = '0' if mode == 'graph_no_overlap' else '1'
         model = _model(dev)
         (opt,), (cfg,) = model.configure_optimizers(tokens_per_batch=B_GLOBAL * L, accumulate_grad_batches=1)
         reducer = GradientAllReducer(model, bucket_mb=4.0)
@@ -83,8 +85,10 @@ def _graph_worker(rank, world, port, out):
         fn = step.eager if mode == 'eager' else step
         torch.manual_seed(99)
         losses[mode] = [float(fn(_batch(dev, rank * per, (rank + 1) * per))) for _ in range(5)]
-        if mode == 'graph':
-            assert step.graph_b is not None
+        if mode != 'eager':
+            assert step.graph_b is not None and step.overlap == (mode == 'graph')
+            # the overlapped mode packs every bucket inside graph A, each followed by an external event
+            assert (len(reducer._capture_order) == len(reducer.buckets)) == step.overlap
         reducer.remove()
     out[rank] = losses
     dist.barrier()
@@ -99,8 +103,9 @@ def test_two_rank_split_graph_step_matches_eager():
         mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         res = dict(out)
     for rank in range(world):
-        for a, b in zip(res[rank]['eager'], res[rank]['graph']):
-            assert abs(a - b) <= 1e-5 * abs(a), res
+        for mode in ('graph', 'graph_no_overlap'):
+            for a, b in zip(res[rank]['eager'], res[rank][mode]):
+                assert abs(a - b) <= 1e-5 * abs(a), (mode, res)
 
 
 def _worker(rank, world, port, out):
