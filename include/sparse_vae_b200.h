@@ -263,6 +263,20 @@ SVAE_API int32_t svae_colsum_counters(int32_t n);
 SVAE_API int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, int64_t ld, float* out, float* workspace,
                 int64_t workspace_floats, uint32_t* counters, void* stream);
 
+/* ---- erf-GELU of the feed-forward blocks (reference core/transformer_layer.py:20-24: nn.GELU() between the two
+ *      ffn projections; core/transformer_language_model.py:58 output_layer) ---- */
+/* x, y, dy, dx: [rows, n] contiguous 16-bit (dtype), n % 8 == 0, 16-byte aligned.  y = x * Phi(x); dx = dy * (Phi(x) +
+ * x * phi(x)), dx may alias dy.  colsum (optional, fp32 [n]): column sums of dx before its 16-bit rounding -- the bias gradient of the
+ * projection that feeds the GELU -- from the same pass; needs `workspace` (svae_gelu_bwd_workspace_floats(rows, n)
+ * floats) and svae_gelu_bwd_counters(n) device uint32 that are ZERO on entry and zero again afterwards (see
+ * svae_colsum).  Deterministic.  Phi is evaluated as 2^-(1 + a Q(a)): |error| <= 2e-6 absolute, 7e-6 relative in the tail. */
+SVAE_API int32_t svae_gelu_supported(int32_t dtype, int64_t rows, int32_t n);
+SVAE_API int svae_gelu_fwd(const void* x, void* y, int32_t dtype, int64_t rows, int32_t n, void* stream);
+SVAE_API int64_t svae_gelu_bwd_workspace_floats(int64_t rows, int32_t n);
+SVAE_API int32_t svae_gelu_bwd_counters(int32_t n);
+SVAE_API int svae_gelu_bwd(const void* dy, const void* x, void* dx, int32_t dtype, int64_t rows, int32_t n, float* colsum,
+                  float* workspace, int64_t workspace_floats, uint32_t* counters, void* stream);
+
 /* ---- rotary position encoding of q / k (reference core/attention.py:194-208) ---- */
 /* x, out: [rows, d_model] contiguous (dtype), row r sits at position r % seq_len; cos / sin tables: [seq_len,
  * d_model/2] (table_dtype) built by the caller with the reference's own ops.  Pairs (2i, 2i+1) are rotated.

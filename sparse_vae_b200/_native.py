@@ -45,6 +45,7 @@ EXPORTS = (
     'svae_dropout_branch_grad', 'svae_bottleneck_fwd_g', 'svae_bottleneck_bwd_g', 'svae_residual_dropout_add_g',
     'svae_dropout_branch_grad_g', 'svae_radam_args_bytes', 'svae_radam_args', 'svae_radam_step_g',
     'svae_xattn_supported', 'svae_xattn_fwd', 'svae_xattn_bwd',
+    'svae_gelu_supported', 'svae_gelu_fwd', 'svae_gelu_bwd_workspace_floats', 'svae_gelu_bwd_counters', 'svae_gelu_bwd',
 )
 
 
@@ -132,6 +133,16 @@ def _load() -> C.CDLL:
     lib.svae_colsum.argtypes = [vp, i32, i64, i32, i64, vp, vp, i64, vp, vp]
     lib.svae_colsum_counters.restype = i32
     lib.svae_colsum_counters.argtypes = [i32]
+    lib.svae_gelu_supported.restype = i32
+    lib.svae_gelu_supported.argtypes = [i32, i64, i32]
+    lib.svae_gelu_fwd.restype = C.c_int
+    lib.svae_gelu_fwd.argtypes = [vp, vp, i32, i64, i32, vp]
+    lib.svae_gelu_bwd_workspace_floats.restype = i64
+    lib.svae_gelu_bwd_workspace_floats.argtypes = [i64, i32]
+    lib.svae_gelu_bwd_counters.restype = i32
+    lib.svae_gelu_bwd_counters.argtypes = [i32]
+    lib.svae_gelu_bwd.restype = C.c_int
+    lib.svae_gelu_bwd.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, i64, vp, vp]
     lib.svae_rotary.restype = C.c_int
     lib.svae_rotary.argtypes = [vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp]
     lib.svae_decode_attn_supported.restype = C.c_int

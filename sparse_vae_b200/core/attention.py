@@ -20,6 +20,7 @@ from torch import nn, Tensor
 
 from .. import _native as N
 from .layer_norm import LayerNorm
+from .gelu import GELU, ffn_forward
 from .linear import Linear, linear3
 from .padded_tensor import split_padding
 from . import cross_attention
@@ -243,7 +244,7 @@ class TransformerLayer(nn.Module):
                  sparse_self_attention: Union[bool, int] = False, learned_queries: int = None):
         super().__init__()
         self.attention = Attention(d_model, num_heads, causal, learned_queries=learned_queries, sparse=sparse_self_attention)
-        self.ffn = nn.Sequential(Linear(d_model, d_model * 4), nn.GELU(), Linear(d_model * 4, d_model, bias=False))
+        self.ffn = nn.Sequential(Linear(d_model, d_model * 4), GELU(), Linear(d_model * 4, d_model, bias=False))
         self.dropout = nn.Dropout(p=0.1)
         self.attn_layer_norm = LayerNorm(d_model)
         self.ffn_layer_norm = LayerNorm(d_model)
@@ -274,7 +275,7 @@ class TransformerLayer(nn.Module):
         h = self.attention(h, h, h, padding=padding)
         if x.shape == h.shape and not (self.cross_attention and context is not None):
             x, h = self.ffn_layer_norm.add_fork(x, h)        # x = x + h and the feed-forward norm, one launch
-            return residual_dropout_add(x, self.ffn(h), self.dropout)
+            return residual_dropout_add(x, ffn_forward(self.ffn, h), self.dropout)
         x = residual_add(x, h) if x.shape == h.shape else h  # learned queries change the length: no residual
 
         if self.cross_attention and context is not None:
@@ -285,7 +286,7 @@ class TransformerLayer(nn.Module):
             x = residual_add(x, h)
 
         x, h = self.ffn_layer_norm.fork(x)
-        return residual_dropout_add(x, self.ffn(h), self.dropout)
+        return residual_dropout_add(x, ffn_forward(self.ffn, h), self.dropout)
 
 
 class Perceiver(nn.Module):

@@ -11,6 +11,7 @@ import torch
 from torch import nn, Tensor
 
 from .attention import Attention, TransformerLayer
+from .gelu import GELU
 from .generation import GenerationState
 from .language_model import LanguageModel, LanguageModelHparams
 from .layer_norm import LayerNorm
@@ -55,7 +56,7 @@ class TransformerLanguageModel(LanguageModel):
         self.context_layer = deepcopy(self.input_layer) if hp.cross_attention and hp.separate_context_embedding else None
 
         logits = nn.Linear(d_model, VOCAB_SIZE)
-        self.output_layer = nn.Sequential(Linear(d_model, d_model), nn.GELU(), LayerNorm(d_model), logits)
+        self.output_layer = nn.Sequential(Linear(d_model, d_model), GELU(), LayerNorm(d_model), logits)
         if hp.tie_embedding_weights and d_embedding == d_model:
             logits.weight = embedding.weight
 

@@ -371,7 +371,7 @@ attn_bwd1_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int start = range_lo; start < range_hi;) {
         const B1Seg s = b1_make_seg(p, g, start, range_hi);
         start += s.t1 - s.t0;
-        int u = 0, normal = 0;
+        int u = 0;
         for (int j = 0; j < s.ntiles; ++j) {
           int kt, ub, ue;
           bool pre;
@@ -383,7 +383,9 @@ attn_bwd1_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             B1_WAIT(W_PREADY, bars + BAR_P_READY + buf, (u >> 1) & 1);      // every phase is observed, in order
             if (slot < 0) continue;                     // the global unit's MMAs belong to warp 15
             if (!pre && !B1_KNOCK(8)) {
-              if (acc == 0 && normal >= 1) B1_WAIT(W_ACCFREE, bars + BAR_ACC_FREE, (normal - 1) & 1);
+              // (the epilogue arrives once per tile, pre-tiles included: it has then seen the previous tile's
+              //  ACC_READY / ACC_READY2 phases, so those barriers can never run two phases ahead of their waiter)
+              if (acc == 0 && j >= 1) B1_WAIT(W_ACCFREE, bars + BAR_ACC_FREE, (j - 1) & 1);
               tc_fence_after();
               const int n = (kt - s.t0) + (slot >> 2);
               const uint32_t q_addr = smem_u32(ring_q(n)) + (slot & 3) * S::SLOT, do_addr = smem_u32(ring_do(n)) + (slot & 3) * S::SLOT;
@@ -400,7 +402,6 @@ attn_bwd1_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tc_commit_w(bars + BAR_A_FREE + buf);
           }
           tc_commit_w(bars + BAR_ACC_READY);
-          if (!pre) ++normal;
         }
         segment_sync();
       }
@@ -597,8 +598,10 @@ attn_bwd1_sm100_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             tma_store_wait_read();
             mbar_arrive(bars + BAR_RING_FREE + n % 3);
           }
-        } else if (tid_g == 0) {
-          mbar_arrive(bars + BAR_K_FREE + (j & 1));
+        } else {                             // pre-tile: nothing to drain
+          tc_fence_before();
+          mbar_arrive_warp(bars + BAR_ACC_FREE);
+          if (tid_g == 0) mbar_arrive(bars + BAR_K_FREE + (j & 1));
         }
         if (pending >= 0) {
           stats_finish(pending);

@@ -119,18 +119,38 @@ __device__ __forceinline__ float slot_max(const uint32_t (&v)[32], float m, bool
   return fmaxf(a0, a1);
 }
 
+// 2^x for two finite x <= 0 on the FMA pipe (no MUFU): Cody-Waite split by the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial of 2^f on [-0.5, 0.5] (relative error 7.5e-5, a sixth of an fp16 half-ulp), the integer part added into
+// the exponent field.  Inputs below -125 are held there (2^-125: nothing for a row sum that contains a 1).
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
+  const float2 r = fadd2(x, splat(12582912.0f));
+  const float2 f = ffma2(fadd2(r, splat(-12582912.0f)), splat(-1.0f), x);
+  float2 p = ffma2(splat(5.517165260e-02f), f, splat(2.426111209e-01f));
+  p = ffma2(p, f, splat(6.932609885e-01f));
+  p = ffma2(p, f, splat(9.999280737e-01f));
+  return make_float2(__int_as_float((__float_as_int(r.x) << 23) + __float_as_int(p.x)),
+                     __int_as_float((__float_as_int(r.y) << 23) + __float_as_int(p.y)));
+}
+
+// Without a padding mask every second pair of exponentials is evaluated on the FMA pipe (exp2_fma2) instead of MUFU.EX2:
+// the exp pass is MUFU-bound (8.2 cycles per warp instruction and SMSP) while the FMA pipe idles.  Causally masked
+// scores (-inf) come out as 2^-125 there instead of 0 -- nothing against a row sum that holds the row's own diagonal
+// key; rows without any finite key only exist with a padding mask, which takes the MUFU-only path below.
 template <typename T>
 __device__ __forceinline__ void slot_exp_pack(const uint32_t (&v)[32], uint32_t (&pk)[16], float& l0, float& l1, bool has_kpm,
                                               const float* kp, float scale_log2, float neg_m) {
   if (!has_kpm) {
+    float2 l = make_float2(l0, l1);
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
-      const float p0 = fast_exp2(fmaf(__uint_as_float(v[c]), scale_log2, neg_m));
-      const float p1 = fast_exp2(fmaf(__uint_as_float(v[c + 1]), scale_log2, neg_m));
-      l0 += p0;
-      l1 += p1;
-      pk[c >> 1] = Elem<T>::pack(p0, p1);
+      const float2 x = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), splat(scale_log2), splat(neg_m));
+      const float2 pe = ((c >> 1) & 1) ? exp2_fma2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+      l = fadd2(l, pe);
+      pk[c >> 1] = Elem<T>::pack(pe.x, pe.y);
     }
+    l0 = l.x;
+    l1 = l.y;
   } else {
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {

@@ -94,6 +94,37 @@ template <> __device__ __forceinline__ float from_f32<float>(float x) { return x
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
 
+// ---- packed fp32 arithmetic of sm_100 (FFMA2 / FMUL2 / FADD2: two lanes per issued instruction) -----------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t pk2(float2 v) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 up2(uint64_t r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+// packed fp32 FMA / MUL of sm_100 (two lanes per instruction)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return up2(d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return up2(d);
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+#endif
+
 inline size_t dtype_size(int dtype) { return dtype == SVAE_DTYPE_F32 ? 4 : 2; }
 
 }  // namespace svae
