@@ -245,7 +245,8 @@ SVAE_API int svae_layernorm_bwd(const void* dy, int32_t y_dtype, const void* x, 
 
 /* ---- vocabulary cross-entropy (reference core/language_model.py:98-113,161-170) ---- */
 /* logits: [rows, vocab] (dtype), row stride ld elements, vocab = 8192*k (k <= 4).  nll[r] = logsumexp(row) -
- * row[labels[r]] (fp32); if write_grad, the row is overwritten with weight[r] * (softmax(row) - onehot(labels[r])).
+ * row[labels[r]] (fp32); if write_grad & 1, the row is overwritten with weight[r] * (softmax(row) - onehot(labels[r]))
+ * (write_grad & 2, 16-bit logits: the one-row-per-CTA kernel instead of the streamed one -- a cross-check for tests).
  * weight[r] == 0 marks an ignored row (nll 0, zero gradient).  One read + one write of the logits. */
 SVAE_API int svae_vocab_ce_supported(int32_t vocab);
 SVAE_API int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t vocab, int64_t ld, const int64_t* labels,

@@ -11,6 +11,7 @@
 // weight[r] = 0 marks an ignored row (label == ignore_index): nll 0, gradient 0.
 // HBM/L2-bound: V * sizeof(T) bytes read + written per row.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace svae {
 
@@ -262,6 +263,159 @@ vocab_ce16_kernel(T* __restrict__ logits, int64_t ld, const int64_t* __restrict_
   }
 }
 
+// ---- 16-bit logits, STREAMED: one persistent CTA per SM, rows through a 3-deep shared-memory ring ---------------
+// The register-resident kernel above alternates per CTA between a load phase, two reduction round trips and a store
+// phase; with two rows per SM in flight HBM idles a third of the time (4.3 TB/s).  Here the row of CTA-iteration i is
+// computed from shared memory while the bulk copies (cp.async.bulk, mbarrier completion) of rows i+1 and i+2 are in
+// flight and the gradient of row i-1 is being written back by a bulk store from the same buffer it arrived in: the
+// memory system always holds two row loads and one row store per SM, independent of the arithmetic.
+constexpr int kCeSThreads = 1024;
+constexpr int kCeSRing = 3;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ptx::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+template <bool A_IS_MAX>
+__device__ __forceinline__ float block_reduce_1024(float a, float* red) {      // red: 32 floats, one use per call site
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oa = __shfl_xor_sync(0xffffffffu, a, o);
+    a = A_IS_MAX ? fmaxf(a, oa) : a + oa;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = a;
+  __syncthreads();
+  a = red[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oa = __shfl_xor_sync(0xffffffffu, a, o);
+    a = A_IS_MAX ? fmaxf(a, oa) : a + oa;
+  }
+  return a;
+}
+
+// V = 8192 * G; thread t owns the 8 elements at (i * 1024 + t) * 8, i < G
+template <typename T, int G>
+__global__ void __launch_bounds__(kCeSThreads, 1)
+vocab_ce16s_kernel(T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, const float* __restrict__ weight,
+                   float* __restrict__ nll, int write_grad, int64_t rows) {
+  constexpr int V = 8192 * G;
+  constexpr uint32_t ROW_BYTES = V * sizeof(T);
+  extern __shared__ uint8_t ce_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ce_smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kCeSRing * ROW_BYTES);
+  float* red = reinterpret_cast<float*>(full + kCeSRing);              // [2][2][32]: max / sum, double-buffered over rows
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kCeSRing; ++b) ptx::mbar_init(full + b, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t mine = first < rows ? (rows - first + stride - 1) / stride : 0;      // rows of this CTA
+  auto row_of = [&](int64_t i) { return first + i * stride; };
+  auto request = [&](int64_t i) {                 // thread 0: bring row i into its ring buffer (ignored rows: nothing to read)
+    const int b = (int)(i % kCeSRing);
+    const int64_t r = row_of(i);
+    if (weight[r] == 0.f) { ptx::mbar_arrive(full + b); return; }
+    ptx::mbar_arrive_expect_tx(full + b, ROW_BYTES);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      bulk_load_1d(smem + (size_t)b * ROW_BYTES + c * (ROW_BYTES / 4), reinterpret_cast<const uint8_t*>(logits + r * ld) + c * (ROW_BYTES / 4),
+                   ROW_BYTES / 4, full + b);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t i = 0; i < mine && i < kCeSRing - 1; ++i) request(i);
+
+  for (int64_t i = 0; i < mine; ++i) {
+    const int b = (int)(i % kCeSRing);
+    const int64_t r = row_of(i);
+    T* buf = reinterpret_cast<T*>(smem + (size_t)b * ROW_BYTES);
+    T* grow = logits + r * ld;
+    const float w = weight[r];
+    float* red_m = red + (i & 1) * 64, *red_s = red_m + 32;
+    ptx::mbar_wait(full + b, (uint32_t)((i / kCeSRing) & 1));
+    if (w == 0.f) {                         // ignored row (block-uniform): nll 0, zero gradient straight to global memory
+      if (threadIdx.x == 0) nll[r] = 0.f;
+      if (write_grad) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) *reinterpret_cast<uint4*>(grow + (k * kCeSThreads + threadIdx.x) * 8) = make_uint4(0, 0, 0, 0);
+      }
+    } else {
+      const int label = (int)labels[r];
+      uint4 raw[G];
+#pragma unroll
+      for (int k = 0; k < G; ++k) raw[k] = *reinterpret_cast<const uint4*>(buf + (k * kCeSThreads + threadIdx.x) * 8);
+      const float x_label = to_f32<T>(buf[label]);
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const uint32_t u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2<T>(u[e]);
+          m = fmaxf(m, fmaxf(f.x, f.y));
+        }
+      }
+      m = block_reduce_1024<true>(m, red_m);
+      const float neg_m2 = -m * kLog2e;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const uint32_t u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2<T>(u[e]);
+          s += ce_exp2(fmaf(f.x, kLog2e, neg_m2)) + ce_exp2(fmaf(f.y, kLog2e, neg_m2));
+        }
+      }
+      s = block_reduce_1024<false>(s, red_s);
+      if (threadIdx.x == 0) nll[r] = (m + log2f(s) * kLn2) - x_label;
+      if (write_grad) {
+        const float scale = w / s;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const uint32_t u[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack2<T>(u[e]);
+            o[e] = pack2<T>(ce_exp2(fmaf(f.x, kLog2e, neg_m2)) * scale, ce_exp2(fmaf(f.y, kLog2e, neg_m2)) * scale);
+          }
+          *reinterpret_cast<uint4*>(buf + (k * kCeSThreads + threadIdx.x) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();                                     // the label's element has been written by its owner
+        if (threadIdx.x == 0)                                // softmax - 1 at the label, rounded once from fp32
+          buf[label] = from_f32<T>(fmaf(ce_exp2(fmaf(x_label, kLog2e, neg_m2)), scale, -w));
+        ptx::fence_proxy_async();                            // generic-proxy writes -> visible to the bulk store
+      }
+    }
+    __syncthreads();                                         // every thread is done with buffer b (and has fenced its writes)
+    if (threadIdx.x == 0) {
+      if (write_grad && w != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          bulk_store_1d(reinterpret_cast<uint8_t*>(grow) + c * (ROW_BYTES / 4), smem + (size_t)b * ROW_BYTES + c * (ROW_BYTES / 4), ROW_BYTES / 4);
+      }
+      ptx::tma_store_commit();
+      // row i + 2 goes into the buffer row i - 1 was stored from: that store (the group before the one just committed)
+      // must have finished READING shared memory
+      if (i + kCeSRing - 1 < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        request(i + kCeSRing - 1);
+      }
+    }
+  }
+  if (threadIdx.x == 0) ptx::tma_store_wait_all();           // the gradient rows are in global memory when the kernel ends
+}
+
 template <typename T>
 static int launch_ce(int k, void* logits, int64_t ld, const int64_t* labels, const float* weight, float* nll, int write_grad,
                      int64_t rows, cudaStream_t st) {
@@ -276,6 +430,27 @@ static int launch_ce(int k, void* logits, int64_t ld, const int64_t* labels, con
 template <typename T>
 static int launch_ce16(int k, void* logits, int64_t ld, const int64_t* labels, const float* weight, float* nll, int write_grad,
                        int64_t rows, cudaStream_t st) {
+  if (k <= 0 || k > 4) return SVAE_ERR_UNSUPPORTED;
+  const int sms = sm_count_of_current_device();
+  const unsigned grid = (unsigned)(rows < sms ? rows : sms);
+#define SVAE_CE16S(KK)                                                                                              \
+  case KK: {                                                                                                        \
+    const size_t smem = (size_t)kCeSRing * 8192 * KK * sizeof(T) + kCeSRing * 8 + 2 * 64 * sizeof(float) + 128;     \
+    auto kern = vocab_ce16s_kernel<T, KK>;                                                                          \
+    SVAE_CONFIGURE_SMEM(kern, (int)smem);                                                                           \
+    kern<<<grid, kCeSThreads, smem, st>>>((T*)logits, ld, labels, weight, nll, write_grad, rows);                   \
+  } break
+  switch (k) { SVAE_CE16S(1); SVAE_CE16S(2); SVAE_CE16S(3); SVAE_CE16S(4); }
+#undef SVAE_CE16S
+  SVAE_CUDA_CHECK(cudaGetLastError());
+  return SVAE_OK;
+}
+
+// the register-resident variant (two CTAs of 512 threads per SM, one row each); kept as the cross-check of the
+// streamed kernel (tests/test_gpu_fused_ce.py)
+template <typename T>
+static int launch_ce16_rows(int k, void* logits, int64_t ld, const int64_t* labels, const float* weight, float* nll, int write_grad,
+                            int64_t rows, cudaStream_t st) {
 #define SVAE_CE16(KK) \
   case KK: vocab_ce16_kernel<T, 2 * KK><<<(unsigned)rows, kCe16Threads, 0, st>>>((T*)logits, ld, labels, weight, nll, write_grad); break
   switch (k) { SVAE_CE16(1); SVAE_CE16(2); SVAE_CE16(3); SVAE_CE16(4); default: return SVAE_ERR_UNSUPPORTED; }
@@ -302,7 +477,13 @@ extern "C" int svae_vocab_ce(void* logits, int32_t dtype, int64_t rows, int32_t 
   ScopedKernelTimer timer("vocab_ce", st);
   const int k = vocab / 8192;
   if (dtype == SVAE_DTYPE_F32) return launch_ce<float>(k, logits, ld, labels, weight, nll, write_grad, rows, st);
-  if (dtype == SVAE_DTYPE_BF16) return launch_ce16<__nv_bfloat16>(k, logits, ld, labels, weight, nll, write_grad, rows, st);
-  if (dtype == SVAE_DTYPE_F16) return launch_ce16<__half>(k, logits, ld, labels, weight, nll, write_grad, rows, st);
+  const bool streamed = !(write_grad & 2);      // bit 1 of write_grad: the register-resident variant (cross-check)
+  write_grad &= 1;
+  if (dtype == SVAE_DTYPE_BF16)
+    return streamed ? launch_ce16<__nv_bfloat16>(k, logits, ld, labels, weight, nll, write_grad, rows, st)
+                    : launch_ce16_rows<__nv_bfloat16>(k, logits, ld, labels, weight, nll, write_grad, rows, st);
+  if (dtype == SVAE_DTYPE_F16)
+    return streamed ? launch_ce16<__half>(k, logits, ld, labels, weight, nll, write_grad, rows, st)
+                    : launch_ce16_rows<__half>(k, logits, ld, labels, weight, nll, write_grad, rows, st);
   SVAE_REQUIRE(false, SVAE_ERR_INVALID, "svae_vocab_ce: dtype %d", dtype);
 }

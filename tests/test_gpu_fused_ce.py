@@ -135,3 +135,43 @@ def test_fused_ce_fp16_autocast():
     assert (h.grad.double().cpu() - hd.grad).abs().max() <= 1e-2 * hd.grad.abs().max()
     assert (lin.weight.grad.double().cpu() - wd.grad).abs().max() <= 1e-2 * wd.grad.abs().max()
     assert (lin.bias.grad.double().cpu() - bd.grad).abs().max() <= 1e-2 * bd.grad.abs().max()
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('rows,V', [(1, 8192), (37, 16384), (149, 32768), (1000, 32768), (300, 24576)])
+def test_streamed_kernel_equals_register_resident_kernel_and_float64(dtype, rows, V):
+    """The streamed 16-bit kernel (persistent CTAs, shared-memory ring, bulk copies) against the one-row-per-CTA
+    kernel (same arithmetic, another summation tree) and against float64."""
+    from sparse_vae_b200 import _native as N
+    g = torch.Generator().manual_seed(rows + V)
+    logits = (torch.randn(rows, V + 8, generator=g) * 3).to('cuda', dtype)[:, :V]          # row stride V + 8
+    labels = torch.randint(1, V, (rows,), generator=g).cuda()
+    weight = torch.rand(rows, generator=g).cuda()
+    weight[::7] = 0.0                                                                         # ignored rows
+    outs = []
+    for variant in (1, 3):                     # write_grad bit 1: the register-resident kernel
+        buf = torch.empty(rows, V + 8, device='cuda', dtype=dtype)
+        buf[:, :V] = logits
+        buf[:, V:] = 7.0                                                                      # must stay untouched
+        nll = torch.full((rows,), -1.0, device='cuda')
+        N.check(N.lib.svae_vocab_ce(buf.data_ptr(), N.svae_dtype(dtype), rows, V, buf.stride(0), labels.data_ptr(),
+                                    weight.data_ptr(), nll.data_ptr(), variant, N.current_stream(buf.device)), 'svae_vocab_ce')
+        torch.cuda.synchronize()
+        assert (buf[:, V:] == 7.0).all()
+        outs.append((buf[:, :V].clone(), nll))
+    # (different summation trees for the row sum: a last-bit difference of the sum moves a rounding now and then)
+    assert (outs[0][0] != outs[1][0]).float().mean().item() < 1e-3
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-5
+    x = logits.double()
+    lse = torch.logsumexp(x, -1)
+    want_nll = torch.where(weight == 0, torch.zeros_like(lse), lse - x.gather(1, labels[:, None])[:, 0])
+    assert (outs[0][1].double() - want_nll).abs().max() <= 1e-5 * want_nll.abs().max() + 1e-5
+    grad = weight.double()[:, None] * (torch.softmax(x, -1) - torch.nn.functional.one_hot(labels, V))
+    tol = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert ((outs[0][0].double() - grad).abs() <= tol * grad.abs() + 1e-7).all()
+    # forward only: the logits stay as they are
+    buf = logits.clone().contiguous()
+    nll = torch.empty(rows, device='cuda')
+    N.check(N.lib.svae_vocab_ce(buf.data_ptr(), N.svae_dtype(dtype), rows, V, buf.stride(0), labels.data_ptr(),
+                                weight.data_ptr(), nll.data_ptr(), 0, N.current_stream(buf.device)), 'svae_vocab_ce')
+    assert torch.equal(buf, logits.contiguous()) and torch.equal(nll, outs[0][1])
