@@ -21,7 +21,7 @@ from torch import nn, Tensor
 from .. import _native as N
 from .layer_norm import LayerNorm
 from .gelu import GELU, ffn_forward
-from .linear import Linear, linear3
+from .linear import Linear, linear3, qkv_rotary
 from .padded_tensor import split_padding
 from . import cross_attention
 from .residual import residual_add, residual_dropout_add
@@ -135,17 +135,29 @@ class Attention(nn.Module):
         if padding is None:
             padding = k_pad
 
+        fused = None
         if self.learned_queries is not None:
             q = self.learned_queries.expand(k.shape[0], *self.learned_queries.shape[1:])
             k, v = self.k_linear(k), self.v_linear(v)
         else:
             q, _ = split_padding(q)
             if q is k and k is v and self.q_linear.bias is not None:        # self-attention: one input, three projections
-                q, k, v = linear3(q, self.q_linear, self.k_linear, self.v_linear)
+                if (N.FUSED_EXTRAS and q.is_cuda and self.cache_index == 0 and not self.kv_cache_length and q.ndim >= 2
+                        and torch.is_autocast_enabled('cuda')):
+                    # projections + rotary as one node (one rotation launch for q and k; its backward also yields the
+                    # q / k bias gradients)
+                    cos, sin = _cached_tables(q.shape[-2], q.shape[-1] // 2, 0, max_pos, torch.get_autocast_dtype('cuda'), q.device)
+                    fused = qkv_rotary(q, self.q_linear, self.k_linear, self.v_linear, cos, sin)
+                if fused is None:
+                    q, k, v = linear3(q, self.q_linear, self.k_linear, self.v_linear)
             else:
                 q, k, v = self.q_linear(q), self.k_linear(k), self.v_linear(v)
-            q = encode_position_rotary(q, self.cache_index, max_pos=max_pos)
-        k = encode_position_rotary(k, self.cache_index, max_pos=max_pos)
+            if fused is not None:
+                q, k, v = fused
+            else:
+                q = encode_position_rotary(q, self.cache_index, max_pos=max_pos)
+        if fused is None:
+            k = encode_position_rotary(k, self.cache_index, max_pos=max_pos)
         if self.kv_cache_length:
             k, v = self._update_kv_cache(k, v)
         if padding is not None and padding.shape[-1] != k.shape[-2]:

@@ -132,6 +132,111 @@ class _Linear3Fn(torch.autograd.Function):
         return (dx.view(x16.shape).to(xd) if dx is not None else None, None, None, *grads)
 
 
+def rotary_pair(a: Tensor, b: Tensor, cos: Tensor, sin: Tensor, conj: bool = False, want_colsum: bool = False):
+    """Both tensors ([..., L, d] contiguous, same shape) rotated by one launch of `svae_rotary_pair`; with
+    `want_colsum` also the fp32 column sums of the two results (bit-identical to `colsum` of them)."""
+    a, b = a.contiguous(), b.contiguous()
+    oa, ob = torch.empty_like(a), torch.empty_like(b)
+    L, d = a.shape[-2], a.shape[-1]
+    rows = a.numel() // d
+    stream = N.current_stream(a.device)
+    sa = sb = ws = counters = None
+    ws_floats = 0
+    if want_colsum:
+        sa = torch.empty(d, device=a.device, dtype=torch.float32)
+        sb = torch.empty(d, device=a.device, dtype=torch.float32)
+        ws_floats = N.lib.svae_rotary_pair_workspace_floats(rows, d)
+        ws = torch.empty(ws_floats, device=a.device, dtype=torch.float32)
+        key = (a.device, stream)
+        counters = _COLSUM_COUNTERS.get(key)
+        if counters is None or counters.numel() < N.lib.svae_colsum_counters(d):
+            counters = _COLSUM_COUNTERS[key] = torch.zeros(max(1024, N.lib.svae_colsum_counters(d)), device=a.device,
+                                                           dtype=torch.int32)
+    N.check(N.lib.svae_rotary_pair(a.data_ptr(), b.data_ptr(), cos.data_ptr(), sin.data_ptr(), oa.data_ptr(), ob.data_ptr(),
+                                   N.svae_dtype(a.dtype), N.svae_dtype(cos.dtype), rows, L, d, int(conj),
+                                   sa.data_ptr() if want_colsum else None, sb.data_ptr() if want_colsum else None,
+                                   ws.data_ptr() if want_colsum else None, ws_floats,
+                                   counters.data_ptr() if want_colsum else None, stream), 'svae_rotary_pair')
+    return oa, ob, sa, sb
+
+
+class _QkvRotaryFn(torch.autograd.Function):
+    """The q / k / v projections of self-attention AND the rotary encoding of q and k as one autograd node (SURVEY 8f
+    row 1; reference core/attention.py:60-70): three library GEMMs and one rotation launch forward; backward rotates
+    dq and dk back in one launch that also accumulates their column sums (the bias gradients of the q / k
+    projections: no separate pass over them), then the GEMMs of `_Linear3Fn`."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, dtype: torch.dtype, shadows, cos: Tensor, sin: Tensor, *wb):
+        x16 = x.to(dtype)
+        outs, w16s = [], []
+        for i in range(3):
+            w, b, w16, b16 = wb[4 * i:4 * i + 4]
+            if w16 is None:
+                w16, b16 = w.to(dtype), b.to(dtype)
+            w16s.append(w16)
+            outs.append(F.linear(x16, w16, b16))
+        q, k, _, _ = rotary_pair(outs[0], outs[1], cos, sin)
+        ctx.save_for_backward(x16, cos, sin, *w16s)
+        ctx.in_dtypes = (x.dtype, wb[0].dtype, wb[1].dtype)
+        ctx.shadows, ctx.epoch = shadows, (shadows.epoch if shadows is not None else 0)
+        return q, k, outs[2]
+
+    @staticmethod
+    def backward(ctx, gq, gk, gv):
+        x16, cos, sin, *w16s = ctx.saved_tensors
+        if ctx.shadows is not None and ctx.shadows.epoch != ctx.epoch:
+            raise RuntimeError("a weight needed for this backward pass was modified (optimizer step?) after the forward "
+                               "pass that used its 16-bit shadow copy")
+        xd, wd, bd = ctx.in_dtypes
+        need = ctx.needs_input_grad
+        x2 = x16.reshape(-1, x16.shape[-1])
+        sums = [None, None, None]
+        gs = [gq, gk, gv]
+        if gq is not None and gk is not None:
+            want = bool(need[6] or need[10])
+            gs[0], gs[1], sums[0], sums[1] = rotary_pair(gq, gk, cos, sin, conj=True, want_colsum=want)
+        else:                                      # (one of q / k unused downstream: rotate what is there with a zero partner)
+            for i in (0, 1):
+                if gs[i] is not None:
+                    gs[i] = rotary_pair(gs[i], torch.zeros_like(gs[i]), cos, sin, conj=True)[0]
+        dx = None
+        grads = []
+        for i, (g, w16) in enumerate(zip(gs, w16s)):
+            dw = db = None
+            if g is not None:
+                g2 = g.reshape(-1, w16.shape[0])
+                if not g2.is_contiguous():
+                    g2 = g2.contiguous()
+                if need[0]:
+                    if dx is None:
+                        dx = torch.mm(g2, w16)
+                    else:
+                        dx.addmm_(g2, w16)
+                if need[5 + 4 * i]:
+                    dw = torch.mm(g2.t(), x2, out_dtype=torch.float32).to(wd)
+                if need[6 + 4 * i]:
+                    db = (sums[i] if sums[i] is not None else colsum(g2)).to(bd)
+            grads += [dw, db, None, None]
+        return (dx.view(x16.shape).to(xd) if dx is not None else None, None, None, None, None, *grads)
+
+
+def qkv_rotary(x: Tensor, lin_q: 'Linear', lin_k: 'Linear', lin_v: 'Linear', cos: Tensor, sin: Tensor):
+    """(rotary(lin_q(x)), rotary(lin_k(x)), lin_v(x)) as one autograd node, or None where the fused form does not apply
+    (the caller then runs the separate ops)."""
+    if not all(m._fused_ok(x) for m in (lin_q, lin_k, lin_v)):
+        return None
+    dtype = torch.get_autocast_dtype('cuda')
+    if dtype not in (torch.bfloat16, torch.float16) or cos.dtype not in (dtype, torch.float32) or x.shape[-1] % 8:
+        return None
+    args = []
+    shs = [m._active_shadow(dtype) for m in (lin_q, lin_k, lin_v)]
+    use = all(sh is not None for sh in shs)
+    for m, sh in zip((lin_q, lin_k, lin_v), shs):
+        args += [m.weight, m.bias, sh[1] if use else None, sh[2] if use else None]
+    return _QkvRotaryFn.apply(x, dtype, shs[0][0] if use else None, cos, sin, *args)
+
+
 def linear3(x: Tensor, lin0: 'Linear', lin1: 'Linear', lin2: 'Linear'):
     """(lin0(x), lin1(x), lin2(x)) -- the q / k / v projections of self-attention."""
     if all(m._fused_ok(x) for m in (lin0, lin1, lin2)):

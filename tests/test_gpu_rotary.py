@@ -64,3 +64,58 @@ def test_rotary_under_autocast_bit_exact(dtype, shape, max_pos):
     ya.backward(dy)
     yb.backward(dy)
     assert torch.equal(a.grad, b.grad)
+
+
+@pytest.mark.parametrize('dtype,table', [(torch.bfloat16, torch.float32), (torch.float16, torch.float32),
+                                         (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32)])
+@pytest.mark.parametrize('B,L,d', [(1, 32, 8), (2, 96, 520), (3, 4096, 512)])
+def test_rotary_pair_equals_two_launches_and_colsum(dtype, table, B, L, d):
+    """`svae_rotary_pair`: both outputs bit-identical to `svae_rotary`, the column sums bit-identical to `svae_colsum`."""
+    from sparse_vae_b200 import _native as N
+    from sparse_vae_b200.core.linear import colsum, rotary_pair
+    g = torch.Generator().manual_seed(B * L + d)
+    a, b = (torch.randn(B, L, d, generator=g).to('cuda', dtype) for _ in range(2))
+    ang = torch.rand(L, d // 2, generator=g) * 6.0
+    cos, sin = ang.cos().to('cuda', table).contiguous(), ang.sin().to('cuda', table).contiguous()
+
+    def single(x, conj):
+        out = torch.empty_like(x)
+        N.check(N.lib.svae_rotary(x.data_ptr(), cos.data_ptr(), sin.data_ptr(), out.data_ptr(), N.svae_dtype(dtype),
+                                  N.svae_dtype(table), B * L, L, d, conj, N.current_stream(x.device)), 'svae_rotary')
+        return out
+
+    for conj in (0, 1):
+        oa, ob, sa, sb = rotary_pair(a, b, cos, sin, conj=bool(conj), want_colsum=True)
+        assert torch.equal(oa, single(a, conj)) and torch.equal(ob, single(b, conj))
+        assert torch.equal(sa, colsum(oa.view(-1, d))) and torch.equal(sb, colsum(ob.view(-1, d)))
+        pa, pb, none_a, none_b = rotary_pair(a, b, cos, sin, conj=bool(conj))
+        assert torch.equal(pa, oa) and torch.equal(pb, ob) and none_a is None and none_b is None
+
+
+def test_qkv_rotary_node_matches_separate_ops():
+    """core/linear.py `qkv_rotary` against linear3 + two encode_position_rotary calls: same forward bits, same gradients."""
+    from sparse_vae_b200.core.attention import Attention
+    torch.manual_seed(11)
+    att = Attention(512, 8, causal=True, sparse=4).cuda()
+    x = torch.randn(2, 1024, 512, device='cuda')
+    dy = torch.randn(2, 1024, 512, device='cuda').to(torch.bfloat16)
+    res = {}
+    from sparse_vae_b200.core import attention as A
+    for fused in (True, False):
+        xin = x.clone().requires_grad_(True)
+        att.zero_grad()
+        orig = A.qkv_rotary
+        if not fused:
+            A.qkv_rotary = lambda *a, **k: None
+        try:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                y = att(xin, xin, xin)
+            y.backward(dy)
+        finally:
+            A.qkv_rotary = orig
+        res[fused] = (y.detach().clone(), xin.grad.clone(), {n: p.grad.clone() for n, p in att.named_parameters() if p.grad is not None})
+    assert torch.equal(res[True][0], res[False][0])
+    assert torch.equal(res[True][1], res[False][1])
+    assert res[True][2].keys() == res[False][2].keys()
+    for n in res[True][2]:
+        assert torch.equal(res[True][2][n], res[False][2][n]), n
