@@ -180,15 +180,25 @@ class GraphedTrainStep:
                 if self.overlap:
                     # hooks live: every bucket is packed inside the graph as soon as its last gradient exists and an
                     # external event marks the spot; the collectives themselves are issued eagerly after the replay
-                    with torch.cuda.graph(self.graph):
-                        self.reducer.zero_grad()
-                        self.reducer.begin_capture()
-                        with torch.autocast('cuda', dtype=self.autocast_dtype):
-                            out = self.model.training_step(self.static_batch, 0)
-                        out['loss'].backward()
-                        self.reducer.end_capture()     # `.grad` -> bucket views, which graph B reads
-                        self.static_loss = out['loss'].detach()
-                else:
+                    try:
+                        with torch.cuda.graph(self.graph):
+                            self.reducer.zero_grad()
+                            self.reducer.begin_capture()
+                            with torch.autocast('cuda', dtype=self.autocast_dtype):
+                                out = self.model.training_step(self.static_batch, 0)
+                            out['loss'].backward()
+                            self.reducer.end_capture()     # `.grad` -> bucket views, which graph B reads
+                            self.static_loss = out['loss'].detach()
+                    except Exception as exc:               # e.g. a torch build without external events: reduce after graph A
+                        import warnings
+                        warnings.warn(f"overlapped gradient all-reduce could not be captured ({type(exc).__name__}: {exc}); "
+                                      f"reducing after the backward graph instead", RuntimeWarning)
+                        self.reducer._capturing = False
+                        self.overlap = False
+                        self.graph = torch.cuda.CUDAGraph()
+                        self.philox.delta = 0
+                        torch.cuda.synchronize(dev)
+                if not self.overlap:
                     self.reducer.sync = False          # the hooks stay quiet: pack + reduce after the replay
                     try:
                         with torch.cuda.graph(self.graph):

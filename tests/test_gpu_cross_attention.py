@@ -68,9 +68,10 @@ def test_encoder_uses_the_kernel_and_matches_sdpa():
     torch.manual_seed(3)
     model = sv.TransformerVAE(to_attrdict(sv.TransformerVAEHparams(num_layers=4))).to(dev).eval()
     model.initialize_weights()
-    x = torch.randn(2, 1024, 512, device=dev)
-    pad = torch.zeros(2, 1024, dtype=torch.bool, device=dev)
+    x = torch.randn(8, 1024, 512, device=dev)               # 8 x 8 heads = 64 (batch, head) pairs: cross_attention.MIN_PAIRS
+    pad = torch.zeros(8, 1024, dtype=torch.bool, device=dev)
     pad[1, 800:] = True
+    pad[5, 300:] = True
     with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
         N.profile_begin()
         a = model.encoder(x, padding=pad)
