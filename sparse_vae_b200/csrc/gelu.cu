@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const uint4* __restrict__
 // ------------------------------------------------------------------------------------------------ backward (+ column sums)
 // block = 32 column vectors x 8 row lanes walking a slab of rows (the layout of colsum_partial_kernel); dx may alias dy
 template <typename T>
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
+__global__ void __launch_bounds__(256, 4) gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx,
                                                        int64_t rows, int n, float* __restrict__ partial,
                                                        unsigned* __restrict__ counters, float* __restrict__ colsum) {
   __shared__ float red[8][32][9];
@@ -114,18 +114,20 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ dy,
     *reinterpret_cast<uint4*>(dx + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   };
   if (ok) {
+    // software pipeline: the loads of the NEXT pair of rows are in flight while this pair is evaluated (~270 instructions
+    // per thread and pair; without it the warps spent half their time waiting: ncu issue-active 44 %, DRAM 55 %)
     const int64_t step = (int64_t)gridDim.y * 8;
     int64_t r = (int64_t)blockIdx.y * 8 + ry;
-    for (; r + step < rows; r += 2 * step) {
-      const int64_t o0 = r * n + vec * 8, o1 = (r + step) * n + vec * 8;
-      const uint4 g0 = __ldcs(reinterpret_cast<const uint4*>(dy + o0)), v0 = __ldcs(reinterpret_cast<const uint4*>(x + o0));
-      const uint4 g1 = __ldcs(reinterpret_cast<const uint4*>(dy + o1)), v1 = __ldcs(reinterpret_cast<const uint4*>(x + o1));
-      one(g0, v0, o0);
-      one(g1, v1, o1);
-    }
-    if (r < rows) {
-      const int64_t o0 = r * n + vec * 8;
-      one(__ldcs(reinterpret_cast<const uint4*>(dy + o0)), __ldcs(reinterpret_cast<const uint4*>(x + o0)), o0);
+    auto ld = [&](const T* p, int64_t row) {
+      return row < rows ? __ldcs(reinterpret_cast<const uint4*>(p + row * n + vec * 8)) : make_uint4(0, 0, 0, 0);
+    };
+    uint4 g0 = ld(dy, r), v0 = ld(x, r), g1 = ld(dy, r + step), v1 = ld(x, r + step);
+    for (; r < rows; r += 2 * step) {
+      const int64_t rn = r + 2 * step;
+      const uint4 ng0 = ld(dy, rn), nv0 = ld(x, rn), ng1 = ld(dy, rn + step), nv1 = ld(x, rn + step);
+      one(g0, v0, r * n + vec * 8);
+      if (r + step < rows) one(g1, v1, (r + step) * n + vec * 8);
+      g0 = ng0; v0 = nv0; g1 = ng1; v1 = nv1;
     }
   }
   if (colsum == nullptr) return;
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const T* __restrict__ dy,
 static int gelu_slabs(int64_t rows, int n) {
   const int col_blocks = (n / 8 + 31) / 32;
   const int sms = sm_count_of_current_device();
-  int slabs = (sms * 8 + col_blocks - 1) / col_blocks;          // 8 resident blocks of 256 threads per SM
+  int slabs = (sms * 4) / col_blocks;                            // ONE wave: 4 resident blocks of 256 threads per SM (<= 64 registers)
+  if (slabs < 1) slabs = 1;
   const int64_t max_slabs = (rows + 15) / 16;                   // at least two rows per row lane
   if (slabs > max_slabs) slabs = (int)(max_slabs > 0 ? max_slabs : 1);
   return slabs;

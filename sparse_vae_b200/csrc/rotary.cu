@@ -129,10 +129,9 @@ __global__ void __launch_bounds__(256) rotary_pair_kernel(const T* xa, const T* 
   float acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-  auto one = [&](int64_t r) {
+  auto one = [&](int64_t r, const Pack<T, 8>& va, const Pack<T, 8>& vb) {
     const int pos = (int)(r % L);
     const int64_t off = r * d + vec * 8;
-    const Pack<T, 8> va = *reinterpret_cast<const Pack<T, 8>*>(xa + off), vb = *reinterpret_cast<const Pack<T, 8>*>(xb + off);
     const Pack<TT, 4> c = *reinterpret_cast<const Pack<TT, 4>*>(cos_t + (int64_t)pos * half + vec * 4);
     const Pack<TT, 4> s = *reinterpret_cast<const Pack<TT, 4>*>(sin_t + (int64_t)pos * half + vec * 4);
     const Pack<T, 8> ra = rotate8<T, TT>(va, c, s, conj), rb = rotate8<T, TT>(vb, c, s, conj);
@@ -147,13 +146,23 @@ __global__ void __launch_bounds__(256) rotary_pair_kernel(const T* xa, const T* 
     }
   };
   if (ok) {
+    // software pipeline: the tensor loads of the next pair of rows are in flight while this pair is rotated (the rows are
+    // visited, and their values accumulated, in the order of colsum_partial_kernel: r, r + step, r + 2 step, ...)
     const int64_t step = (int64_t)gridDim.y * 8;
     int64_t r = (int64_t)blockIdx.y * 8 + ry;
-    for (; r + step < rows; r += 2 * step) {
-      one(r);
-      one(r + step);
+    auto ld = [&](const T* p, int64_t row) {
+      Pack<T, 8> v;
+      if (row < rows) v = *reinterpret_cast<const Pack<T, 8>*>(p + row * d + vec * 8);
+      return v;
+    };
+    Pack<T, 8> a0 = ld(xa, r), b0 = ld(xb, r), a1 = ld(xa, r + step), b1 = ld(xb, r + step);
+    for (; r < rows; r += 2 * step) {
+      const int64_t rn = r + 2 * step;
+      const Pack<T, 8> na0 = ld(xa, rn), nb0 = ld(xb, rn), na1 = ld(xa, rn + step), nb1 = ld(xb, rn + step);
+      one(r, a0, b0);
+      if (r + step < rows) one(r + step, a1, b1);
+      a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
     }
-    if (r < rows) one(r);
   }
   if constexpr (kSums) {
     const int64_t plane = (int64_t)gridDim.y * d;            // partial: [2][slabs][d]
