@@ -264,6 +264,14 @@ SVAE_API int32_t svae_colsum_counters(int32_t n);
 SVAE_API int svae_colsum(const void* x, int32_t dtype, int64_t rows, int32_t n, int64_t ld, float* out, float* workspace,
                 int64_t workspace_floats, uint32_t* counters, void* stream);
 
+/* ---- weight gradient of the token embedding (reference core/transformer_language_model.py:47-53) ---- */
+/* grad: [n, d] contiguous (dtype); perm: the positions 0..n-1 ordered by token id, equal ids in position order (the
+ * indices of `torch.sort(ids, stable=True)`); bounds: int64 [vocab + 1], bounds[v] = first index of token v in that order
+ * (`torch.searchsorted(sorted_ids, arange(vocab + 1))`); dweight: fp32 [vocab, d], every row written (zeros for absent
+ * tokens).  Row v = sum of grad[perm[j]], bounds[v] <= j < bounds[v + 1], in that order: bit-deterministic, no atomics. */
+SVAE_API int svae_embedding_bwd(const void* grad, int32_t dtype, const int64_t* bounds, const int64_t* perm, int64_t n,
+                       int32_t vocab, int32_t d, float* dweight, void* stream);
+
 /* ---- erf-GELU of the feed-forward blocks (reference core/transformer_layer.py:20-24: nn.GELU() between the two
  *      ffn projections; core/transformer_language_model.py:58 output_layer) ---- */
 /* x, y, dy, dx: [rows, n] contiguous 16-bit (dtype), n % 8 == 0, 16-byte aligned.  y = x * Phi(x); dx = dy * (Phi(x) +

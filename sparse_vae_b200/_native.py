@@ -45,7 +45,7 @@ EXPORTS = (
     'svae_dropout_branch_grad', 'svae_bottleneck_fwd_g', 'svae_bottleneck_bwd_g', 'svae_residual_dropout_add_g',
     'svae_dropout_branch_grad_g', 'svae_radam_args_bytes', 'svae_radam_args', 'svae_radam_step_g',
     'svae_xattn_supported', 'svae_xattn_fwd', 'svae_xattn_bwd',
-    'svae_rotary_pair_workspace_floats', 'svae_rotary_pair',
+    'svae_rotary_pair_workspace_floats', 'svae_rotary_pair', 'svae_embedding_bwd',
     'svae_gelu_supported', 'svae_gelu_fwd', 'svae_gelu_bwd_workspace_floats', 'svae_gelu_bwd_counters', 'svae_gelu_bwd',
 )
 
@@ -138,6 +138,8 @@ def _load() -> C.CDLL:
     lib.svae_rotary_pair_workspace_floats.argtypes = [i64, i32]
     lib.svae_rotary_pair.restype = C.c_int
     lib.svae_rotary_pair.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, i64, vp, vp]
+    lib.svae_embedding_bwd.restype = C.c_int
+    lib.svae_embedding_bwd.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, vp]
     lib.svae_gelu_supported.restype = i32
     lib.svae_gelu_supported.argtypes = [i32, i64, i32]
     lib.svae_gelu_fwd.restype = C.c_int

@@ -11,6 +11,7 @@ import torch
 from torch import nn, Tensor
 
 from .attention import Attention, TransformerLayer
+from .embedding import Embedding
 from .gelu import GELU
 from .generation import GenerationState
 from .language_model import LanguageModel, LanguageModelHparams
@@ -48,7 +49,7 @@ class TransformerLanguageModel(LanguageModel):
         d_model = hp.d_model
         d_embedding = hp.d_embedding or d_model
 
-        embedding = nn.Embedding(VOCAB_SIZE, d_embedding)
+        embedding = Embedding(VOCAB_SIZE, d_embedding)
         layers = [embedding, nn.Dropout(p=hp.input_dropout)]
         if d_embedding != d_model:
             layers.insert(1, nn.Linear(d_embedding, d_model))
