@@ -300,11 +300,14 @@ SVAE_API int svae_rotary(const void* x, const void* cos_table, const void* sin_t
  * (both or neither; fp32 [d_model]): column sums of the two outputs, bit-identical to svae_colsum of them -- the bias
  * gradients of the q / k projections when the launch is the backward rotation (conj = 1) of dq / dk.  workspace:
  * svae_rotary_pair_workspace_floats(rows, d_model) floats; counters: svae_colsum_counters(d_model) ZEROED device
- * uint32, zero again afterwards.  xa may equal oa (in place), likewise xb / ob. */
+ * uint32, zero again afterwards.  in_ld / out_ld: row strides (elements, >= d_model, multiples of 8) of the inputs /
+ * outputs, so q and k may be column slices of one [rows, 3 d_model] projection output or gradient buffer.  xa may equal
+ * oa (in place, in_ld == out_ld), likewise xb / ob. */
 SVAE_API int64_t svae_rotary_pair_workspace_floats(int64_t rows, int32_t d_model);
 SVAE_API int svae_rotary_pair(const void* xa, const void* xb, const void* cos_table, const void* sin_table, void* oa, void* ob,
                      int32_t dtype, int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj,
-                     float* sum_a, float* sum_b, float* workspace, int64_t workspace_floats, uint32_t* counters, void* stream);
+                     int64_t in_ld, int64_t out_ld, float* sum_a, float* sum_b, float* workspace, int64_t workspace_floats,
+                     uint32_t* counters, void* stream);
 
 /* ---- token-by-token decoding ----------------------------------------------------------------
  * One sparse-attention layer's step of TransformerVAE.sample (reference transformer_vae.py:112-126 ->

@@ -137,7 +137,7 @@ def _load() -> C.CDLL:
     lib.svae_rotary_pair_workspace_floats.restype = i64
     lib.svae_rotary_pair_workspace_floats.argtypes = [i64, i32]
     lib.svae_rotary_pair.restype = C.c_int
-    lib.svae_rotary_pair.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, vp, vp, vp, i64, vp, vp]
+    lib.svae_rotary_pair.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, i32, i32, i32, i64, i64, vp, vp, vp, i64, vp, vp]
     lib.svae_embedding_bwd.restype = C.c_int
     lib.svae_embedding_bwd.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp, vp]
     lib.svae_gelu_supported.restype = i32

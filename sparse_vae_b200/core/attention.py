@@ -168,7 +168,7 @@ class Attention(nn.Module):
 
         if sparse and self.key_cache is None:
             kpm = padding * -1e7 if padding is not None else None
-            out = sparse(q, k, v, key_padding_mask=kpm)                                 # [B, H, L, Dh] over [B, L, H, Dh]
+            out = sparse(q, k, v, key_padding_mask=kpm, joint_grads=fused is not None)  # [B, H, L, Dh] over [B, L, H, Dh]
         elif (N.FUSED_EXTRAS and not self.causal and self.key_cache is None and (padding is None or padding.ndim == 2)
               and cross_attention.supported(q, k, v)):
             # the Perceiver encoder's learned queries (<= 64) over the whole sequence: K and V streamed once through

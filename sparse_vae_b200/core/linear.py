@@ -132,13 +132,33 @@ class _Linear3Fn(torch.autograd.Function):
         return (dx.view(x16.shape).to(xd) if dx is not None else None, None, None, *grads)
 
 
-def rotary_pair(a: Tensor, b: Tensor, cos: Tensor, sin: Tensor, conj: bool = False, want_colsum: bool = False):
-    """Both tensors ([..., L, d] contiguous, same shape) rotated by one launch of `svae_rotary_pair`; with
-    `want_colsum` also the fp32 column sums of the two results (bit-identical to `colsum` of them)."""
-    a, b = a.contiguous(), b.contiguous()
-    oa, ob = torch.empty_like(a), torch.empty_like(b)
+def _row_stride(t: Tensor):
+    """Row stride (elements) if `t` [..., L, d] is a uniformly strided stack of rows with unit inner stride, else None."""
+    if t.stride(-1) != 1 or t.ndim < 2:
+        return None
+    ld = t.stride(-2)
+    for i in range(t.ndim - 2):
+        if t.shape[i] > 1 and t.stride(i) != t.stride(i + 1) * t.shape[i + 1]:
+            return None
+    return ld if ld >= t.shape[-1] and ld % 8 == 0 and t.data_ptr() % 16 == 0 else None
+
+
+def rotary_pair(a: Tensor, b: Tensor, cos: Tensor, sin: Tensor, conj: bool = False, want_colsum: bool = False,
+                inplace: bool = False):
+    """Both tensors ([..., L, d], same shape and row stride -- e.g. column slices of one [..., L, 3 d] buffer) rotated by
+    one launch of `svae_rotary_pair`; with `want_colsum` also the fp32 column sums of the two results (bit-identical to
+    `colsum` of them).  `inplace` rotates the rows where they are; otherwise the results are new contiguous tensors."""
+    ld_a, ld_b = _row_stride(a), _row_stride(b)
+    if ld_a is None or ld_a != ld_b:
+        assert not inplace, "in-place rotation needs uniformly strided rows"
+        a, b = a.contiguous(), b.contiguous()
+        ld_a = a.shape[-1]
     L, d = a.shape[-2], a.shape[-1]
     rows = a.numel() // d
+    if inplace:
+        oa, ob, out_ld = a, b, ld_a
+    else:
+        oa, ob, out_ld = torch.empty(a.shape, dtype=a.dtype, device=a.device), torch.empty(b.shape, dtype=b.dtype, device=b.device), d
     stream = N.current_stream(a.device)
     sa = sb = ws = counters = None
     ws_floats = 0
@@ -153,34 +173,54 @@ def rotary_pair(a: Tensor, b: Tensor, cos: Tensor, sin: Tensor, conj: bool = Fal
             counters = _COLSUM_COUNTERS[key] = torch.zeros(max(1024, N.lib.svae_colsum_counters(d)), device=a.device,
                                                            dtype=torch.int32)
     N.check(N.lib.svae_rotary_pair(a.data_ptr(), b.data_ptr(), cos.data_ptr(), sin.data_ptr(), oa.data_ptr(), ob.data_ptr(),
-                                   N.svae_dtype(a.dtype), N.svae_dtype(cos.dtype), rows, L, d, int(conj),
+                                   N.svae_dtype(a.dtype), N.svae_dtype(cos.dtype), rows, L, d, int(conj), ld_a, out_ld,
                                    sa.data_ptr() if want_colsum else None, sb.data_ptr() if want_colsum else None,
                                    ws.data_ptr() if want_colsum else None, ws_floats,
                                    counters.data_ptr() if want_colsum else None, stream), 'svae_rotary_pair')
     return oa, ob, sa, sb
 
 
+def _adjacent(ts, numel_each: int) -> bool:
+    """Three contiguous 16-bit tensors that sit back to back in one allocation."""
+    return all(t is not None and t.is_contiguous() and t.numel() == numel_each for t in ts) and \
+        all(ts[i + 1].data_ptr() == ts[i].data_ptr() + numel_each * ts[i].element_size() for i in range(2)) and \
+        ts[0].untyped_storage().data_ptr() == ts[2].untyped_storage().data_ptr()
+
+
 class _QkvRotaryFn(torch.autograd.Function):
     """The q / k / v projections of self-attention AND the rotary encoding of q and k as one autograd node (SURVEY 8f
-    row 1; reference core/attention.py:60-70): three library GEMMs and one rotation launch forward; backward rotates
-    dq and dk back in one launch that also accumulates their column sums (the bias gradients of the q / k
-    projections: no separate pass over them), then the GEMMs of `_Linear3Fn`."""
+    row 1; reference core/attention.py:60-70).  With the 16-bit weight shadows of the three layers back to back (they
+    are: `WeightShadows` lays them out that way) the projections are ONE library GEMM [rows, d] x [d, 3 d] forward; q and
+    k are rotated out of its output by one launch, v stays a column slice of it.  Backward: the attention backward
+    writes dq | dk | dv into one [rows, 3 d] buffer (`joint_grads`), dq and dk are rotated back in place by one launch
+    that also accumulates their column sums (the q / k bias gradients), and the input and weight gradients are one
+    GEMM each (89 / 78 / 91 us against 114 / 123 / 124 us for three of each at [65536, 512]).  Without adjacent
+    shadows or a joint gradient buffer it is the three-GEMM form of `_Linear3Fn` around the same rotation launch."""
 
     @staticmethod
     def forward(ctx, x: Tensor, dtype: torch.dtype, shadows, cos: Tensor, sin: Tensor, *wb):
         x16 = x.to(dtype)
-        outs, w16s = [], []
+        w16s, b16s = [], []
         for i in range(3):
             w, b, w16, b16 = wb[4 * i:4 * i + 4]
             if w16 is None:
                 w16, b16 = w.to(dtype), b.to(dtype)
             w16s.append(w16)
-            outs.append(F.linear(x16, w16, b16))
-        q, k, _, _ = rotary_pair(outs[0], outs[1], cos, sin)
+            b16s.append(b16)
+        d_out, d_in = w16s[0].shape
+        joint = _adjacent(w16s, d_out * d_in) and _adjacent(b16s, d_out) and d_out % 8 == 0
+        if joint:
+            w_cat = torch.as_strided(w16s[0], (3 * d_out, d_in), (d_in, 1))
+            b_cat = torch.as_strided(b16s[0], (3 * d_out,), (1,))
+            qkv = F.linear(x16, w_cat, b_cat)
+            q0, k0, v = qkv[..., :d_out], qkv[..., d_out:2 * d_out], qkv[..., 2 * d_out:]
+        else:
+            q0, k0, v = (F.linear(x16, w16, b16) for w16, b16 in zip(w16s, b16s))
+        q, k, _, _ = rotary_pair(q0, k0, cos, sin)
         ctx.save_for_backward(x16, cos, sin, *w16s)
         ctx.in_dtypes = (x.dtype, wb[0].dtype, wb[1].dtype)
         ctx.shadows, ctx.epoch = shadows, (shadows.epoch if shadows is not None else 0)
-        return q, k, outs[2]
+        return q, k, v
 
     @staticmethod
     def backward(ctx, gq, gk, gv):
@@ -191,6 +231,28 @@ class _QkvRotaryFn(torch.autograd.Function):
         xd, wd, bd = ctx.in_dtypes
         need = ctx.needs_input_grad
         x2 = x16.reshape(-1, x16.shape[-1])
+        d_out, d_in = w16s[0].shape
+        # ---- one [rows, 3 d] gradient buffer (attention backward with joint_grads) and adjacent weights: one GEMM each
+        # (adjacency is checked on the tensors at hand: under activation checkpointing the saved weights are those of the
+        #  recomputed forward, which runs outside `WeightShadows.step()` and casts each weight separately)
+        if (_adjacent(w16s, d_out * d_in) and gq is not None and gk is not None and gv is not None and all(need[5 + i] for i in range(0, 12, 4))
+                and all(need[6 + i] for i in range(0, 12, 4)) and not (gq.requires_grad or gk.requires_grad or gv.requires_grad)):
+            ld = _row_stride(gq)
+            if (ld == 3 * d_out and _row_stride(gk) == ld and _row_stride(gv) == ld and gq.dtype == gk.dtype == gv.dtype == x16.dtype
+                    and gk.data_ptr() == gq.data_ptr() + d_out * gq.element_size()
+                    and gv.data_ptr() == gk.data_ptr() + d_out * gq.element_size()):
+                rows = x2.shape[0]
+                _, _, sum_q, sum_k = rotary_pair(gq, gk, cos, sin, conj=True, want_colsum=True, inplace=True)
+                dqkv = torch.as_strided(gq, (rows, 3 * d_out), (ld, 1))
+                w_cat = torch.as_strided(w16s[0], (3 * d_out, d_in), (d_in, 1))
+                dx = torch.mm(dqkv, w_cat).view(x16.shape).to(xd) if need[0] else None
+                dw = torch.mm(dqkv.t(), x2, out_dtype=torch.float32)
+                sum_v = colsum(torch.as_strided(gv, (rows, d_out), (ld, 1)))
+                grads = []
+                for i, sm in enumerate((sum_q, sum_k, sum_v)):
+                    grads += [dw[i * d_out:(i + 1) * d_out].to(wd), sm.to(bd), None, None]
+                return (dx, None, None, None, None, *grads)
+        # ---- three GEMM pairs
         sums = [None, None, None]
         gs = [gq, gk, gv]
         if gq is not None and gk is not None:
@@ -305,8 +367,12 @@ class WeightShadows:
         mods = [m for m in self.root.modules() if isinstance(m, Linear) and m.weight.is_cuda
                 and m.weight.dtype == torch.float32 and m.weight.is_contiguous()]
         params, index = [], {}
-        for m in mods:
-            for t in (m.weight, m.bias):
+        # all weights first (module order), then all biases: the q / k / v weights of an attention layer -- consecutive
+        # modules of equal shape -- sit back to back, and so do their biases, which lets `_QkvRotaryFn` run the three
+        # projections as one GEMM on a [3 d, d] view
+        for pick in (lambda m: m.weight, lambda m: m.bias):
+            for m in mods:
+                t = pick(m)
                 if t is not None and id(t) not in index and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
                     index[id(t)] = len(params)
                     params.append(t)

@@ -63,7 +63,8 @@ def _make_desc(cfg: 'SparseAttention', q, k, v, out, flags=0, scale=None) -> N.A
 
 class _SparseAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, kpm, cfg, flags):
+    def forward(ctx, q, k, v, kpm, cfg, flags, joint_grads=False):
+        ctx.joint_grads = bool(joint_grads)
         q, k, v = _kernel_ready(q), _kernel_ready(k), _kernel_ready(v)
         B, H, L, Dh = q.shape
         out = _new_blhd(B, H, L, Dh, q)
@@ -82,7 +83,13 @@ class _SparseAttentionFn(torch.autograd.Function):
         cfg = ctx.cfg
         B, H, L, Dh = q.shape
         dout = _kernel_ready(dout)
-        dq, dk, dv = (_new_blhd(B, H, L, Dh, q) for _ in range(3))
+        if ctx.joint_grads:
+            # one [B, L, 3 * H * Dh] buffer = [dq | dk | dv] per row: the q / k / v projections' backward then runs ONE
+            # input-gradient GEMM and ONE weight-gradient GEMM on it (core/linear.py `_QkvRotaryFn`)
+            joint = torch.empty(B, L, 3, H, Dh, dtype=q.dtype, device=q.device)
+            dq, dk, dv = (joint[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        else:
+            dq, dk, dv = (_new_blhd(B, H, L, Dh, q) for _ in range(3))
         desc = _make_desc(cfg, q, k, v, out, ctx.flags)
         desc.do_stride, desc.dq_stride = _strides3(dout), _strides3(dq)
         desc.dk_stride, desc.dv_stride = _strides3(dk), _strides3(dv)
@@ -99,7 +106,7 @@ class _SparseAttentionFn(torch.autograd.Function):
             N.check(N.lib.svae_attn_bwd(ctypes.byref(desc), N.ptr(q), N.ptr(k), N.ptr(v), N.ptr(out), N.ptr(dout),
                                         N.ptr(lse), N.ptr(kpm), N.ptr(dq), N.ptr(dk), N.ptr(dv), ws_ptr, ws_bytes,
                                         N.current_stream(q.device)), 'svae_attn_bwd')
-        return dq, dk, dv, None, None, None
+        return dq, dk, dv, None, None, None, None
 
 
 # Frozen and therefore hashable, like the reference's (used as an lru_cache key there and here)
@@ -136,7 +143,7 @@ class SparseAttention:
         return int(N.lib.svae_layout_nnz(num_blocks, self.window_size, int(self.causal), int(self.include_cls)))
 
     # ---- the op ------------------------------------------------------------------------------------------------
-    def __call__(self, q, k, v, attn_mask=None, key_padding_mask=None, *, force_exact: bool = False):
+    def __call__(self, q, k, v, attn_mask=None, key_padding_mask=None, *, force_exact: bool = False, joint_grads: bool = False):
         seq_len = q.shape[-2]
         assert seq_len == k.shape[-2] == v.shape[-2]    # Self-attention
         assert seq_len <= self.max_seq_len
@@ -162,7 +169,7 @@ class SparseAttention:
             flags |= N.ATTN_PERSISTENT
         if _env_flag('SVAE_ATTN_BWD_TWO_PASS', False):      # cross-check of the one-pass backward (tests)
             flags |= N.ATTN_BWD_TWO_PASS
-        out = _SparseAttentionFn.apply(q, k, v, kpm, self, flags)
+        out = _SparseAttentionFn.apply(q, k, v, kpm, self, flags, joint_grads)
         for _ in range(4 - original_dims):
             out = out.squeeze(0)
         return out

@@ -62,9 +62,9 @@ __device__ __forceinline__ Pack<T, 8> rotate8(const Pack<T, 8>& xv, const Pack<T
 //   matmul's autocast cast applies); backward = autograd of the promoted products: each fp32 product is cast back
 //   to T and the two contributions are summed in T.
 template <typename T, typename TT>
-__global__ void __launch_bounds__(256) rotary_kernel(const T* __restrict__ x, const TT* __restrict__ cos_t,
-                                                      const TT* __restrict__ sin_t, T* __restrict__ out, int64_t rows, int L,
-                                                      int d, int conj) {
+__global__ void __launch_bounds__(256) rotary_kernel(const T* x, const TT* __restrict__ cos_t,      // (x may alias out)
+                                                      const TT* __restrict__ sin_t, T* out, int64_t rows, int L,
+                                                      int d, int conj, int64_t in_ld, int64_t out_ld) {
   const int vec_per_row = d >> 3;
   const int64_t total = rows * vec_per_row;
   const int half = d >> 1;
@@ -72,10 +72,10 @@ __global__ void __launch_bounds__(256) rotary_kernel(const T* __restrict__ x, co
     const int64_t r = i / vec_per_row;
     const int vcol = (int)(i - r * vec_per_row);
     const int pos = (int)(r % L);
-    const Pack<T, 8> xv = *reinterpret_cast<const Pack<T, 8>*>(x + r * d + vcol * 8);
+    const Pack<T, 8> xv = *reinterpret_cast<const Pack<T, 8>*>(x + r * in_ld + vcol * 8);
     const Pack<TT, 4> c = *reinterpret_cast<const Pack<TT, 4>*>(cos_t + (int64_t)pos * half + vcol * 4);
     const Pack<TT, 4> s = *reinterpret_cast<const Pack<TT, 4>*>(sin_t + (int64_t)pos * half + vcol * 4);
-    *reinterpret_cast<Pack<T, 8>*>(out + r * d + vcol * 8) = rotate8<T, TT>(xv, c, s, conj);
+    *reinterpret_cast<Pack<T, 8>*>(out + r * out_ld + vcol * 8) = rotate8<T, TT>(xv, c, s, conj);
   }
 }
 
@@ -122,7 +122,8 @@ __device__ __forceinline__ Pack<T, 8> rotate8(const Pack<T, 8>& xv, const Pack<T
 template <typename T, typename TT, bool kSums>
 __global__ void __launch_bounds__(256) rotary_pair_kernel(const T* xa, const T* xb,      // (may alias oa / ob: no __restrict__)
                                                            const TT* __restrict__ cos_t, const TT* __restrict__ sin_t,
-                                                           T* oa, T* ob, int64_t rows, int L, int d, int conj,
+                                                           T* oa, T* ob, int64_t rows, int L, int d, int conj, int64_t in_ld,
+                                                           int64_t out_ld,
                                                            float* __restrict__ partial, unsigned* __restrict__ counters,
                                                            float* __restrict__ sum_a, float* __restrict__ sum_b) {
   __shared__ float red[kSums ? 8 : 1][32][17];
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) rotary_pair_kernel(const T* xa, const T* 
   for (int e = 0; e < 16; ++e) acc[e] = 0.f;
   auto one = [&](int64_t r, const Pack<T, 8>& va, const Pack<T, 8>& vb) {
     const int pos = (int)(r % L);
-    const int64_t off = r * d + vec * 8;
+    const int64_t off = r * out_ld + vec * 8;
     const Pack<TT, 4> c = *reinterpret_cast<const Pack<TT, 4>*>(cos_t + (int64_t)pos * half + vec * 4);
     const Pack<TT, 4> s = *reinterpret_cast<const Pack<TT, 4>*>(sin_t + (int64_t)pos * half + vec * 4);
     const Pack<T, 8> ra = rotate8<T, TT>(va, c, s, conj), rb = rotate8<T, TT>(vb, c, s, conj);
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(256) rotary_pair_kernel(const T* xa, const T* 
     int64_t r = (int64_t)blockIdx.y * 8 + ry;
     auto ld = [&](const T* p, int64_t row) {
       Pack<T, 8> v;
-      if (row < rows) v = *reinterpret_cast<const Pack<T, 8>*>(p + row * d + vec * 8);
+      if (row < rows) v = *reinterpret_cast<const Pack<T, 8>*>(p + row * in_ld + vec * 8);
       return v;
     };
 #if SVAE_ROTARY_PIPELINE
@@ -237,25 +238,26 @@ static int rotary_pair_slabs(int64_t rows, int n) {
 
 template <typename T, typename TT>
 static int launch_rotary_pair(const void* xa, const void* xb, const void* c, const void* s, void* oa, void* ob, int64_t rows, int L,
-                              int d, int conj, float* partial, unsigned* counters, float* sum_a, float* sum_b, cudaStream_t st) {
+                              int d, int conj, int64_t in_ld, int64_t out_ld, float* partial, unsigned* counters, float* sum_a,
+                              float* sum_b, cudaStream_t st) {
   dim3 grid((d / 8 + 31) / 32, rotary_pair_slabs(rows, d));
   if (sum_a)
     rotary_pair_kernel<T, TT, true><<<grid, 256, 0, st>>>((const T*)xa, (const T*)xb, (const TT*)c, (const TT*)s, (T*)oa, (T*)ob, rows, L, d,
-                                                          conj, partial, counters, sum_a, sum_b);
+                                                          conj, in_ld, out_ld, partial, counters, sum_a, sum_b);
   else
     rotary_pair_kernel<T, TT, false><<<grid, 256, 0, st>>>((const T*)xa, (const T*)xb, (const TT*)c, (const TT*)s, (T*)oa, (T*)ob, rows, L,
-                                                           d, conj, nullptr, nullptr, nullptr, nullptr);
+                                                           d, conj, in_ld, out_ld, nullptr, nullptr, nullptr, nullptr);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
 
 template <typename T, typename TT>
 static int launch_rotary(const void* x, const void* c, const void* s, void* out, int64_t rows, int L, int d, int conj,
-                         cudaStream_t st) {
+                         int64_t in_ld, int64_t out_ld, cudaStream_t st) {
   const int64_t total = rows * (d >> 3);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  rotary_kernel<T, TT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const TT*)c, (const TT*)s, (T*)out, rows, L, d, conj);
+  rotary_kernel<T, TT><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, (const TT*)c, (const TT*)s, (T*)out, rows, L, d, conj, in_ld, out_ld);
   SVAE_CUDA_CHECK(cudaGetLastError());
   return SVAE_OK;
 }
@@ -264,9 +266,19 @@ static int launch_rotary(const void* x, const void* c, const void* s, void* out,
 
 using namespace svae;
 
+static int rotary_ld(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype, int32_t table_dtype,
+                     int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, int64_t in_ld, int64_t out_ld, void* stream);
+
 extern "C" int svae_rotary(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype,
                            int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, void* stream) {
+  return rotary_ld(x, cos_table, sin_table, out, dtype, table_dtype, rows, seq_len, d_model, conj, d_model, d_model, stream);
+}
+
+static int rotary_ld(const void* x, const void* cos_table, const void* sin_table, void* out, int32_t dtype, int32_t table_dtype,
+                     int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj, int64_t in_ld, int64_t out_ld, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(in_ld >= d_model && out_ld >= d_model && in_ld % 8 == 0 && out_ld % 8 == 0, SVAE_ERR_INVALID,
+               "svae_rotary: row strides must be >= d_model and multiples of 8");
   SVAE_REQUIRE(x && cos_table && sin_table && out && rows >= 0, SVAE_ERR_INVALID, "svae_rotary: null argument");
   SVAE_REQUIRE(d_model > 0 && d_model % 8 == 0 && seq_len > 0 && rows % seq_len == 0, SVAE_ERR_INVALID,
                "svae_rotary: d_model must be a multiple of 8 and rows a multiple of seq_len");
@@ -278,7 +290,7 @@ extern "C" int svae_rotary(const void* x, const void* cos_table, const void* sin
                SVAE_ERR_INVALID, "svae_rotary: misaligned tensor");
   if (rows == 0) return SVAE_OK;
   ScopedKernelTimer timer("rotary", st);
-#define SVAE_ROT(T, TT) return launch_rotary<T, TT>(x, cos_table, sin_table, out, rows, seq_len, d_model, conj, st)
+#define SVAE_ROT(T, TT) return launch_rotary<T, TT>(x, cos_table, sin_table, out, rows, seq_len, d_model, conj, in_ld, out_ld, st)
   if (dtype == SVAE_DTYPE_F32) SVAE_ROT(float, float);
   if (dtype == SVAE_DTYPE_BF16) { if (table_dtype == dtype) SVAE_ROT(__nv_bfloat16, __nv_bfloat16); SVAE_ROT(__nv_bfloat16, float); }
   if (dtype == SVAE_DTYPE_F16) { if (table_dtype == dtype) SVAE_ROT(__half, __half); SVAE_ROT(__half, float); }
@@ -292,9 +304,11 @@ extern "C" int64_t svae_rotary_pair_workspace_floats(int64_t rows, int32_t d_mod
 
 extern "C" int svae_rotary_pair(const void* xa, const void* xb, const void* cos_table, const void* sin_table, void* oa, void* ob,
                                 int32_t dtype, int32_t table_dtype, int64_t rows, int32_t seq_len, int32_t d_model, int32_t conj,
-                                float* sum_a, float* sum_b, float* workspace, int64_t workspace_floats, uint32_t* counters,
-                                void* stream) {
+                                int64_t in_ld, int64_t out_ld, float* sum_a, float* sum_b, float* workspace, int64_t workspace_floats,
+                                uint32_t* counters, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SVAE_REQUIRE(in_ld >= d_model && out_ld >= d_model && in_ld % 8 == 0 && out_ld % 8 == 0, SVAE_ERR_INVALID,
+               "svae_rotary_pair: row strides must be >= d_model and multiples of 8");
   SVAE_REQUIRE(xa && xb && cos_table && sin_table && oa && ob && rows >= 0, SVAE_ERR_INVALID, "svae_rotary_pair: null argument");
   SVAE_REQUIRE(d_model > 0 && d_model % 8 == 0 && seq_len > 0 && rows % seq_len == 0, SVAE_ERR_INVALID,
                "svae_rotary_pair: d_model must be a multiple of 8 and rows a multiple of seq_len");
@@ -311,12 +325,13 @@ extern "C" int svae_rotary_pair(const void* xa, const void* xb, const void* cos_
                  "svae_rotary_pair: column sums need svae_rotary_pair_workspace_floats() floats and zeroed counters");
   if (rows == 0) return SVAE_OK;
   if (!sum_a) {      // no column sums: the flat one-tensor kernel twice (57.6 us against 61.6 us for the slab layout at [65536, 512])
-    const int rc = svae_rotary(xa, cos_table, sin_table, oa, dtype, table_dtype, rows, seq_len, d_model, conj, stream);
-    return rc ? rc : svae_rotary(xb, cos_table, sin_table, ob, dtype, table_dtype, rows, seq_len, d_model, conj, stream);
+    const int rc = rotary_ld(xa, cos_table, sin_table, oa, dtype, table_dtype, rows, seq_len, d_model, conj, in_ld, out_ld, stream);
+    return rc ? rc : rotary_ld(xb, cos_table, sin_table, ob, dtype, table_dtype, rows, seq_len, d_model, conj, in_ld, out_ld, stream);
   }
   ScopedKernelTimer timer("rotary", st);
 #define SVAE_ROTP(T, TT) \
-  return launch_rotary_pair<T, TT>(xa, xb, cos_table, sin_table, oa, ob, rows, seq_len, d_model, conj, workspace, counters, sum_a, sum_b, st)
+  return launch_rotary_pair<T, TT>(xa, xb, cos_table, sin_table, oa, ob, rows, seq_len, d_model, conj, in_ld, out_ld, workspace, counters, \
+                                   sum_a, sum_b, st)
   if (dtype == SVAE_DTYPE_F32) SVAE_ROTP(float, float);
   if (dtype == SVAE_DTYPE_BF16) { if (table_dtype == dtype) SVAE_ROTP(__nv_bfloat16, __nv_bfloat16); SVAE_ROTP(__nv_bfloat16, float); }
   if (dtype == SVAE_DTYPE_F16) { if (table_dtype == dtype) SVAE_ROTP(__half, __half); SVAE_ROTP(__half, float); }

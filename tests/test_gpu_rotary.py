@@ -119,3 +119,44 @@ def test_qkv_rotary_node_matches_separate_ops():
     assert res[True][2].keys() == res[False][2].keys()
     for n in res[True][2]:
         assert torch.equal(res[True][2][n], res[False][2][n]), n
+
+
+def test_qkv_joint_gemm_path_matches_separate_ops():
+    """With the 16-bit weight shadows active the three projections run as ONE GEMM forward and one input- / one
+    weight-gradient GEMM backward on the attention backward's joint [dq | dk | dv] buffer: same numbers as the separate
+    ops up to the GEMMs' summation order."""
+    from sparse_vae_b200.core import attention as A
+    from sparse_vae_b200.core.attention import Attention
+    from sparse_vae_b200.core.linear import WeightShadows
+    torch.manual_seed(12)
+    att = Attention(512, 8, causal=True, sparse=4).cuda()
+    shadows = WeightShadows(att)
+    x = torch.randn(2, 2048, 512, device='cuda')
+    dy = torch.randn(2, 2048, 512, device='cuda').to(torch.bfloat16)
+    res = {}
+    for fused in (True, False):
+        xin = x.clone().requires_grad_(True)
+        att.zero_grad()
+        orig = A.qkv_rotary
+        if not fused:
+            A.qkv_rotary = lambda *a, **k: None
+        try:
+            with torch.autocast('cuda', dtype=torch.bfloat16), shadows.step():
+                y = att(xin, xin, xin)
+            y.backward(dy)
+        finally:
+            A.qkv_rotary = orig
+        grads = {n: p.grad.clone() for n, p in att.named_parameters() if p.grad is not None}
+        if fused:      # the joint path ran: the three weight gradients are row blocks of one [3 d, d] GEMM result
+            gq, gk, gv = (getattr(att, n).weight.grad for n in ('q_linear', 'k_linear', 'v_linear'))
+            assert gk.data_ptr() == gq.data_ptr() + gq.numel() * 4 and gv.data_ptr() == gk.data_ptr() + gk.numel() * 4
+        res[fused] = (y.detach().float(), xin.grad.clone(), grads)
+
+    def close(a, b, tol):
+        return (a.float() - b.float()).abs().max().item() <= tol * b.float().abs().max().item()
+
+    assert close(res[True][0], res[False][0], 1e-2)
+    assert close(res[True][1], res[False][1], 1e-2)
+    assert res[True][2].keys() == res[False][2].keys()
+    for n in res[True][2]:
+        assert close(res[True][2][n], res[False][2][n], 1e-2), n
