@@ -14,8 +14,8 @@ namespace svae {
 
 constexpr int kMtChunk = 65536;        // elements per CTA
 constexpr int kMtThreads = 512;
-constexpr int kMtMaxTensors = 24;
-constexpr int kMtMaxBlocks = 320;
+constexpr int kMtMaxTensors = 120;      // (tables of ~13 KB: kernel parameters may be up to 32 KB on sm_70+ with CUDA >= 12.1)
+constexpr int kMtMaxBlocks = 1600;
 
 template <int NPTR>
 struct MtTable {
