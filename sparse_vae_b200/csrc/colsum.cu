@@ -11,14 +11,18 @@ namespace svae {
 
 template <typename T> struct Vec8;      // 8 consecutive elements (16 bytes for 16-bit types, 32 for fp32)
 template <> struct Vec8<float> {
-  static __device__ __forceinline__ void add(const float* p, float (&acc)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load(const float* p) {
+    return Raw{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+  }
+  static __device__ __forceinline__ void add(const Raw& r, float (&acc)[8]) {
+    acc[0] += r.a.x; acc[1] += r.a.y; acc[2] += r.a.z; acc[3] += r.a.w; acc[4] += r.b.x; acc[5] += r.b.y; acc[6] += r.b.z; acc[7] += r.b.w;
   }
 };
 template <> struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void add(const __nv_bfloat16* p, float (&acc)[8]) {
-    const uint4 t = *reinterpret_cast<const uint4*>(p);
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void add(const Raw& t, float (&acc)[8]) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -28,8 +32,9 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 template <> struct Vec8<__half> {
-  static __device__ __forceinline__ void add(const __half* p, float (&acc)[8]) {
-    const uint4 t = *reinterpret_cast<const uint4*>(p);
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw load(const __half* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void add(const Raw& t, float (&acc)[8]) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -51,11 +56,13 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   if (ok) {
     const int64_t step = (int64_t)gridDim.y * 8;
     int64_t r = (int64_t)blockIdx.y * 8 + ry;
-    for (; r + step < rows; r += 2 * step) {         // two independent loads in flight
-      Vec8<T>::add(x + r * ld + vec * 8, acc);
-      Vec8<T>::add(x + (r + step) * ld + vec * 8, acc);
+#pragma unroll 2
+    for (; r + 3 * step < rows; r += 4 * step) {     // four independent loads in flight, added in row order
+      typename Vec8<T>::Raw a = Vec8<T>::load(x + r * ld + vec * 8), b = Vec8<T>::load(x + (r + step) * ld + vec * 8);
+      typename Vec8<T>::Raw c = Vec8<T>::load(x + (r + 2 * step) * ld + vec * 8), d = Vec8<T>::load(x + (r + 3 * step) * ld + vec * 8);
+      Vec8<T>::add(a, acc); Vec8<T>::add(b, acc); Vec8<T>::add(c, acc); Vec8<T>::add(d, acc);
     }
-    if (r < rows) Vec8<T>::add(x + r * ld + vec * 8, acc);
+    for (; r < rows; r += step) Vec8<T>::add(Vec8<T>::load(x + r * ld + vec * 8), acc);
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[ry][cx][e] = acc[e];
