@@ -47,5 +47,31 @@ for p_ in params:
     p_.grad = torch.randn_like(p_)
 FusedGradClipper()([p_.grad for p_ in params], 1.0)
 RAdam(params, lr=1e-3).step()
+# ---- kernels of round 2: GELU (odd row counts: the prefetch of the software pipeline runs past the last row), rotary
+#      pair on column slices with column sums, embedding gradient (skewed ids), the fused feed-forward / q-k-v nodes
+from sparse_vae_b200.core.attention import Attention  # noqa: E402
+from sparse_vae_b200.core.embedding import Embedding  # noqa: E402
+from sparse_vae_b200.core.gelu import GELU, ffn_forward, gelu_backward, gelu_forward  # noqa: E402
+from sparse_vae_b200.core.linear import WeightShadows, rotary_pair  # noqa: E402
+for rows, n in ((1, 8), (37, 24), (1001, 520), (4099, 2048)):
+    xg = torch.randn(rows, n, device=dev).to(torch.bfloat16)
+    gelu_forward(xg)
+    gelu_backward(torch.randn_like(xg), xg, want_colsum=True)
+    gelu_backward(torch.randn_like(xg), xg, inplace=True)
+buf = torch.randn(3, 96, 3 * 520, device=dev).to(torch.bfloat16)
+ang = torch.rand(96, 260, device=dev) * 6
+rotary_pair(buf[..., :520], buf[..., 520:1040], ang.cos(), ang.sin(), conj=True, want_colsum=True, inplace=True)
+rotary_pair(buf[..., :520], buf[..., 520:1040], ang.cos(), ang.sin())
+emb = Embedding(1000, 64).to(dev)
+ids = torch.randint(0, 1000, (5, 333), device=dev)
+ids[ids % 3 == 0] = 7
+emb(ids).sum().backward()
+ffn = torch.nn.Sequential(Linear(512, 2048), GELU(), Linear(2048, 512, bias=False)).to(dev)
+att = Attention(512, 8, causal=True, sparse=4).to(dev)
+shadows = WeightShadows(torch.nn.ModuleList([ffn, att]))
+xa = torch.randn(2, 1024, 512, device=dev, requires_grad=True)
+with torch.autocast('cuda', dtype=torch.bfloat16), shadows.step():
+    y = ffn_forward(ffn, xa) + att(xa, xa, xa)
+y.float().sum().backward()
 torch.cuda.synchronize()
 print('sanitize_small: all kernels ran')
