@@ -50,7 +50,7 @@ class Embedding(nn.Embedding):
         w = self.weight
         if (N.FUSED_EXTRAS and w.is_cuda and ids.is_cuda and w.dtype == torch.float32 and w.requires_grad
                 and torch.is_grad_enabled() and ids.dtype == torch.int64 and self.padding_idx is None and self.max_norm is None
-                and not self.scale_grad_by_freq and not self.sparse and w.shape[1] % 4 == 0 and ids.numel() > 0
+                and not self.scale_grad_by_freq and not self.sparse and w.shape[1] % 4 == 0 and ids.numel() > 0 and w.shape[0] < 2 ** 31 - 1
                 and w.is_contiguous()):
             return _EmbeddingFn.apply(ids, w)
         return super().forward(ids)

@@ -89,6 +89,39 @@ def test_drop_in_modules_on_cpu_are_the_torch_modules():
         assert lin(x).dtype == torch.bfloat16           # plain nn.Linear behaviour under CPU autocast
 
 
+def test_round2_drop_in_modules_on_cpu_are_the_torch_modules():
+    from sparse_vae_b200.core.embedding import Embedding
+    from sparse_vae_b200.core.gelu import GELU, ffn_forward
+    from sparse_vae_b200.core.linear import Linear
+    gelu, emb = GELU(), Embedding(50, 8)
+    assert isinstance(gelu, torch.nn.GELU) and isinstance(emb, torch.nn.Embedding)
+    assert set(gelu.state_dict()) == set() and set(emb.state_dict()) == {'weight'}
+    x = torch.randn(3, 5, 16)
+    assert torch.equal(gelu(x), F.gelu(x))
+    ids = torch.randint(0, 50, (4, 7))
+    y = emb(ids)
+    assert torch.equal(y, F.embedding(ids, emb.weight)) and type(y.grad_fn).__name__ == 'EmbeddingBackward0'
+    ffn = torch.nn.Sequential(Linear(16, 64), GELU(), Linear(64, 16, bias=False))
+    assert torch.equal(ffn_forward(ffn, x), ffn(x))             # CPU tensors: the plain Sequential
+
+
+def test_row_stride_and_adjacency_helpers():
+    from sparse_vae_b200.core.linear import _adjacent, _row_stride
+    buf = torch.zeros(2, 6, 48, dtype=torch.bfloat16)
+    q, k, v = buf[..., :16], buf[..., 16:32], buf[..., 32:]
+    assert _row_stride(buf) == 48 and _row_stride(q) == 48 and _row_stride(k) == 48 and _row_stride(v) == 48
+    assert _row_stride(buf.transpose(0, 1)) is None              # rows of different batches are not uniformly spaced
+    assert _row_stride(buf[..., ::2]) is None                    # inner stride 2
+    assert _row_stride(buf[..., 4:20]) is None                   # slice start not 16-byte aligned
+    flat = torch.zeros(3 * 32 + 8, dtype=torch.bfloat16)
+    a, b, c = (flat[i * 32:(i + 1) * 32].view(4, 8) for i in range(3))
+    assert _adjacent([a, b, c], 32)
+    assert not _adjacent([a, c, b], 32) and not _adjacent([a, b, None], 32)
+    assert not _adjacent([a, b, torch.zeros(4, 8, dtype=torch.bfloat16)], 32)
+    w_cat = torch.as_strided(a, (12, 8), (8, 1))
+    assert w_cat.data_ptr() == a.data_ptr() and torch.equal(w_cat[4:8], b)
+
+
 def test_fused_paths_refuse_cpu_tensors():
     from sparse_vae_b200.core.fused_ce import fused_vocab_nll, supported
     lin = torch.nn.Linear(8, 8192)
