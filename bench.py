@@ -54,7 +54,7 @@ WINDOW = 4            # TransformerVAEHparams().sparse_self_attention window (Sp
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=['c2', 'c4', 'c5'],
